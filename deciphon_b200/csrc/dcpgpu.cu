@@ -1,0 +1,1057 @@
+// dcpgpu.cu -- the C ABI of include/dcpgpu.h over the sm_100a kernels.
+//
+// Host side of the boundary described in include/dcpgpu.h: profile residency
+// (work_setup/protein_setup_viterbi, c-core/work.c:24-46, protein.c:353-394), read
+// packing (batch_encode, c-core/batch.c:60), per-window special transitions
+// (xtrans_setup, c-core/xtrans.c:21-68) and the launches of the score and trace kernels.
+// No CPU compute path exists here: every entry point needs a CUDA device.
+#include "../../include/dcpgpu.h"
+#include "generic_kernel.cuh"
+#include "layout.cuh"
+#include "score_kernel.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace dcp;
+
+namespace {
+
+struct Slab
+{
+  char *base;
+  size_t size;
+  size_t used;
+};
+
+struct PoolBlock
+{
+  float *em;    // [n][1364] log-probs
+  float *trans; // [n][7]
+  int64_t first;
+  int64_t n;
+};
+
+struct NodeRef
+{
+  float const *em;
+  float const *trans;
+};
+
+} // namespace
+
+struct dcpgpu_ctx
+{
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+
+  std::vector<Slab> slabs;
+  size_t profile_bytes = 0;
+
+  std::vector<PoolBlock> pool;
+  int64_t pool_nodes = 0;
+
+  std::vector<ProfileDesc> h_profiles;
+  ProfileDesc *d_profiles = nullptr;
+  size_t d_profiles_cap = 0;
+  bool profiles_dirty = false;
+
+  // upload staging (device)
+  char *d_stage = nullptr;
+  size_t d_stage_cap = 0;
+
+  // reads
+  uint32_t *d_words = nullptr;
+  long long *d_seq_word = nullptr;
+  int *d_seq_len = nullptr;
+  std::vector<int> h_seq_len;
+  int nseq = 0;
+  int maxlen = 0;
+
+  // special transitions per flag combination
+  float *d_xt[4] = {nullptr, nullptr, nullptr, nullptr};
+  int xt_len[4] = {-1, -1, -1, -1};
+
+  // score pass state
+  float2 *d_out = nullptr;
+  size_t out_cap = 0;
+  int64_t last_n = 0;
+  unsigned long long *d_counters = nullptr; // [16] work cursors + [16] = nhits
+  int *d_class_profiles = nullptr;
+  size_t class_profiles_cap = 0;
+  Pair *d_pairs = nullptr;
+  size_t pairs_cap = 0;
+  long long *d_order = nullptr;
+  size_t order_cap = 0;
+  float *d_scratch = nullptr;
+  size_t scratch_cap = 0; // floats
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  double last_cells = 0;
+  int64_t last_launches = 0;
+
+  // trace pass state
+  std::vector<Pair> t_pairs;
+  Pair *d_tpairs = nullptr;
+  uint32_t *d_xnodes = nullptr;
+  uint16_t *d_nodes = nullptr;
+  long long *d_xnode_off = nullptr, *d_node_off = nullptr, *d_step_off = nullptr;
+  int *d_nsteps = nullptr;
+  float2 *d_tout = nullptr;
+  std::vector<long long> t_xnode_off, t_node_off;
+  std::vector<int> t_nsteps;
+  bool traced = false;
+};
+
+namespace {
+
+int fail_cuda(dcpgpu_ctx *c, cudaError_t e, char const *what)
+{
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+  if (c) c->err = buf;
+  return e == cudaErrorMemoryAllocation ? DCPGPU_ENOMEM : DCPGPU_ECUDA;
+}
+
+int fail(dcpgpu_ctx *c, int code, char const *what)
+{
+  if (c) c->err = what;
+  return code;
+}
+
+#define CU(call)                                                                                 \
+  do                                                                                             \
+  {                                                                                              \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail_cuda(ctx, e_, #call);                                     \
+  } while (0)
+
+template <class T>
+int ensure(dcpgpu_ctx *ctx, T *&ptr, size_t &cap, size_t need)
+{
+  if (need <= cap && ptr) return 0;
+  if (ptr) CU(cudaFree(ptr));
+  ptr = nullptr;
+  cap = 0;
+  size_t n = std::max<size_t>(need, 16);
+  CU(cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
+  cap = n;
+  return 0;
+}
+
+int arena_alloc(dcpgpu_ctx *ctx, size_t bytes, void **out)
+{
+  bytes = (bytes + 255) & ~size_t(255);
+  for (auto &s : ctx->slabs)
+    if (s.size - s.used >= bytes)
+    {
+      *out = s.base + s.used;
+      s.used += bytes;
+      ctx->profile_bytes += bytes;
+      return 0;
+    }
+  size_t const slab = std::max<size_t>(bytes, size_t(512) << 20);
+  char *p = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&p), slab));
+  ctx->slabs.push_back({p, slab, bytes});
+  ctx->profile_bytes += bytes;
+  *out = p;
+  return 0;
+}
+
+// ---- pack kernels: .dcp log-probs -> cost-form device layout (protein.c:353-394) -------
+
+__global__ void pack_em_kernel(NodeRef const *nodes, int K, int Q, int VL, int Kpad, float *em)
+{
+  // x: node index over Kpad, y: code
+  int const k = blockIdx.x * blockDim.x + threadIdx.x;
+  int const code = blockIdx.y;
+  if (k >= Kpad) return;
+  float v = CUDART_INF_F;
+  if (k < K) v = -nodes[k].em[code]; // viterbi_set_match(v, -emission[i], k, i), protein.c:390-391
+  em[(size_t)code * Kpad + layout_pos(k, Q, VL)] = v;
+}
+
+__global__ void pack_core_kernel(NodeRef const *nodes, float const *BMk, int K, int Q, int VL, int Kpad,
+                                 float *core)
+{
+  int const k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= Kpad) return;
+  float v[C_ROWS];
+#pragma unroll
+  for (int i = 0; i < C_ROWS; ++i)
+    v[i] = CUDART_INF_F;
+  if (k < K)
+  {
+    v[C_BM] = -BMk[k]; // protein.c:361-364
+    if (k >= 1)
+    { // transitions out of node k-1 land on node k (protein.c:374-381)
+      float const *t = nodes[k - 1].trans;
+      v[C_MM] = -t[0];
+      v[C_MD] = -t[2];
+      v[C_IM] = -t[3];
+      v[C_DM] = -t[5];
+      v[C_DD] = -t[6];
+    }
+    if (k + 1 < K)
+    { // MI, II stay on node k; node K-1 keeps +INF (protein.c:382-383)
+      float const *t = nodes[k].trans;
+      v[C_MI] = -t[1];
+      v[C_II] = -t[4];
+    }
+  }
+  int const pos = layout_pos(k, Q, VL);
+#pragma unroll
+  for (int i = 0; i < C_ROWS; ++i)
+    core[(size_t)i * Kpad + pos] = v[i];
+}
+
+__global__ void pack_nulbg_kernel(float const *nul, float const *bg, float2 *out)
+{
+  int const c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < NCODES) out[c] = make_float2(-nul[c], -bg[c]); // protein.c:387-388
+}
+
+__global__ void hits_fill_kernel(float2 const *out, long long n, unsigned long long *cursor,
+                                 long long cap, long long *idx)
+{
+  long long const i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float2 const v = out[i];
+  float const d = v.y - v.x;
+  if (d <= 0.0f && d > -CUDART_INF_F)
+  {
+    unsigned long long const at = atomicAdd(cursor, 1ULL);
+    if ((long long)at < cap) idx[at] = i;
+  }
+}
+
+// The special transitions of one window (xtrans.c:21-68 with thread.c:112's max(L/3, 1)).
+// Same expressions as the reference: float operands, double log(), results stored to float.
+void host_xtrans(int window_len, bool multi_hits, bool hmmer3_compat, float *out)
+{
+  int seq_size = window_len / 3;
+  if (seq_size < 1) seq_size = 1;
+  float const L = (float)seq_size;
+  float q = 0.0f;
+  float log_q = -INFINITY;
+  if (multi_hits)
+  {
+    q = 0.5f;
+    log_q = (float)::log(0.5);
+  }
+  float const denom = L + 2 + q / (1 - q);
+  float const lp = (float)(::log((double)L) - ::log((double)denom));
+  float const l1p = (float)(::log((double)(2 + q / (1 - q))) - ::log((double)denom));
+  float const lr = (float)(::log((double)L) - ::log((double)(L + 1)));
+  float NN = lp, CC = lp, JJ = lp;
+  float const NB = l1p, CT = l1p, JB = l1p, RR = lr, EJ = log_q;
+  float const EC = (float)::log((double)(1 - q));
+  if (hmmer3_compat) NN = CC = JJ = ::logf(1.0f);
+  out[X_RR] = -RR;
+  out[X_SN] = -0 - NN;
+  out[X_NN] = -NN;
+  out[X_SB] = -0 - NB;
+  out[X_NB] = -NB;
+  out[X_EB] = -EJ - JB;
+  out[X_JB] = -JB;
+  out[X_EJ] = -EJ - JJ;
+  out[X_JJ] = -JJ;
+  out[X_EC] = -EC - CC;
+  out[X_CC] = -CC;
+  out[X_ET] = -EC - CT;
+  out[X_CT] = -CT;
+}
+
+int ensure_xt(dcpgpu_ctx *ctx, uint32_t flags, int maxlen)
+{
+  int const f = (int)(flags & 3u);
+  if (ctx->xt_len[f] >= maxlen && ctx->d_xt[f]) return 0;
+  int const n = std::max(maxlen, 1);
+  std::vector<float> h((size_t)(n + 1) * X_STRIDE, 0.0f);
+  for (int L = 1; L <= n; ++L)
+    host_xtrans(L, flags & DCPGPU_MULTI_HITS, flags & DCPGPU_HMMER3_COMPAT, &h[(size_t)L * X_STRIDE]);
+  if (ctx->d_xt[f]) CU(cudaFree(ctx->d_xt[f]));
+  ctx->d_xt[f] = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xt[f]), h.size() * sizeof(float)));
+  CU(cudaMemcpyAsync(ctx->d_xt[f], h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->xt_len[f] = n;
+  return 0;
+}
+
+int sync_profiles(dcpgpu_ctx *ctx)
+{
+  if (!ctx->profiles_dirty) return 0;
+  size_t const n = ctx->h_profiles.size();
+  if (n > ctx->d_profiles_cap)
+  {
+    if (ctx->d_profiles) CU(cudaFree(ctx->d_profiles));
+    ctx->d_profiles = nullptr;
+    size_t const cap = std::max<size_t>(n * 2, 1024);
+    CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_profiles), cap * sizeof(ProfileDesc)));
+    ctx->d_profiles_cap = cap;
+  }
+  CU(cudaMemcpyAsync(ctx->d_profiles, ctx->h_profiles.data(), n * sizeof(ProfileDesc),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->profiles_dirty = false;
+  return 0;
+}
+
+int kernel_class(ProfileDesc const &p) { return (p.W == 1 && p.Q <= MAXQ_REG) ? p.Q : 0; }
+
+template <int Q>
+int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
+{
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q>, SCORE_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned long long const want = (a.nitems + (SCORE_THREADS / 32) - 1) / (SCORE_THREADS / 32);
+  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
+  score_reg_kernel<Q><<<grid, SCORE_THREADS, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->last_launches += 1;
+  return 0;
+}
+
+int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
+{
+  switch (cls)
+  {
+  case 1: return launch_reg<1>(ctx, a);
+  case 2: return launch_reg<2>(ctx, a);
+  case 3: return launch_reg<3>(ctx, a);
+  case 4: return launch_reg<4>(ctx, a);
+  case 5: return launch_reg<5>(ctx, a);
+  case 6: return launch_reg<6>(ctx, a);
+  case 7: return launch_reg<7>(ctx, a);
+  case 8: return launch_reg<8>(ctx, a);
+  default: return fail(ctx, DCPGPU_EINVAL, "bad kernel class");
+  }
+}
+
+template <bool TRACE>
+int launch_generic(dcpgpu_ctx *ctx, GenArgs a, int max_K)
+{
+  int const KG = (max_K + 31) & ~31;
+  size_t const stride = (size_t)19 * KG;
+  unsigned long long const want = (a.s.nitems + GEN_WARPS - 1) / GEN_WARPS;
+  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)4 * ctx->sm_count);
+  size_t const need = stride * GEN_WARPS * grid;
+  int rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, need);
+  if (rc) return rc;
+  a.scratch = ctx->d_scratch;
+  a.scratch_stride = stride;
+  generic_kernel<TRACE><<<grid, GEN_THREADS, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->last_launches += 1;
+  return 0;
+}
+
+ReadsView reads_view(dcpgpu_ctx const *ctx)
+{
+  ReadsView r;
+  r.words = ctx->d_words;
+  r.seq_word = ctx->d_seq_word;
+  r.seq_len = ctx->d_seq_len;
+  r.nseq = ctx->nseq;
+  return r;
+}
+
+int begin_pass(dcpgpu_ctx *ctx, size_t npairs)
+{
+  int rc = sync_profiles(ctx);
+  if (rc) return rc;
+  if ((rc = ensure(ctx, ctx->d_out, ctx->out_cap, npairs))) return rc;
+  CU(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), ctx->stream));
+  ctx->last_launches = 0;
+  ctx->last_cells = 0;
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+
+int end_pass(dcpgpu_ctx *ctx, int64_t npairs)
+{
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->last_n = npairs;
+  return 0;
+}
+
+} // namespace
+
+// ---- C ABI -------------------------------------------------------------------------------
+
+extern "C" {
+
+char const *dcpgpu_strerror(int code)
+{
+  switch (code)
+  {
+  case DCPGPU_OK: return "ok";
+  case DCPGPU_ENODEVICE: return "no CUDA device available (deciphon_b200 has no CPU fallback)";
+  case DCPGPU_ECUDA: return "CUDA call failed";
+  case DCPGPU_ENOMEM: return "out of memory";
+  case DCPGPU_EINVAL: return "invalid argument";
+  case DCPGPU_ESTATE: return "call made in the wrong state";
+  default: return "unknown dcpgpu error";
+  }
+}
+
+char const *dcpgpu_last_error(dcpgpu_ctx const *ctx) { return ctx ? ctx->err.c_str() : ""; }
+
+int dcpgpu_open(dcpgpu_ctx **out, int device)
+{
+  if (!out) return DCPGPU_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return DCPGPU_ENODEVICE;
+  if (device < 0 || device >= ndev) return DCPGPU_EINVAL;
+  dcpgpu_ctx *ctx = new (std::nothrow) dcpgpu_ctx;
+  if (!ctx) return DCPGPU_ENOMEM;
+  ctx->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_counters), 32 * sizeof(unsigned long long));
+  if (e != cudaSuccess)
+  {
+    delete ctx;
+    return DCPGPU_ECUDA;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void dcpgpu_close(dcpgpu_ctx *ctx)
+{
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto &s : ctx->slabs) cudaFree(s.base);
+  for (auto &b : ctx->pool) { cudaFree(b.em); cudaFree(b.trans); }
+  cudaFree(ctx->d_profiles);
+  cudaFree(ctx->d_stage);
+  cudaFree(ctx->d_words);
+  cudaFree(ctx->d_seq_word);
+  cudaFree(ctx->d_seq_len);
+  for (auto p : ctx->d_xt) cudaFree(p);
+  cudaFree(ctx->d_out);
+  cudaFree(ctx->d_counters);
+  cudaFree(ctx->d_class_profiles);
+  cudaFree(ctx->d_pairs);
+  cudaFree(ctx->d_order);
+  cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_tpairs);
+  cudaFree(ctx->d_xnodes);
+  cudaFree(ctx->d_nodes);
+  cudaFree(ctx->d_xnode_off);
+  cudaFree(ctx->d_node_off);
+  cudaFree(ctx->d_step_off);
+  cudaFree(ctx->d_nsteps);
+  cudaFree(ctx->d_tout);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int dcpgpu_set_stream(dcpgpu_ctx *ctx, void *cuda_stream)
+{
+  if (!ctx) return DCPGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream && ctx->stream) CU(cudaStreamDestroy(ctx->stream));
+  if (cuda_stream)
+  {
+    ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+    ctx->own_stream = false;
+  }
+  else
+  {
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return 0;
+}
+
+int dcpgpu_sync(dcpgpu_ctx *ctx)
+{
+  if (!ctx) return DCPGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int64_t dcpgpu_device_info(dcpgpu_ctx const *ctx, int what)
+{
+  if (!ctx) return -1;
+  size_t fr = 0, tot = 0;
+  switch (what)
+  {
+  case 0: return ctx->sm_count;
+  case 1:
+  case 2:
+    cudaSetDevice(ctx->device);
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return -1;
+    return (int64_t)(what == 1 ? tot : fr);
+  case 3: return (int64_t)ctx->profile_bytes;
+  default: return -1;
+  }
+}
+
+int dcpgpu_pool_add(dcpgpu_ctx *ctx, int nnodes, float const *emission, float const *trans,
+                    int64_t *first_node_id)
+{
+  if (!ctx || nnodes <= 0 || !emission || !trans) return fail(ctx, DCPGPU_EINVAL, "pool_add: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  PoolBlock b{nullptr, nullptr, ctx->pool_nodes, nnodes};
+  size_t const eb = (size_t)nnodes * NCODES * sizeof(float), tb = (size_t)nnodes * 7 * sizeof(float);
+  CU(cudaMalloc(reinterpret_cast<void **>(&b.em), eb));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&b.trans), tb);
+  if (e != cudaSuccess)
+  {
+    cudaFree(b.em);
+    return fail_cuda(ctx, e, "cudaMalloc(pool trans)");
+  }
+  ctx->pool.push_back(b);
+  ctx->pool_nodes += nnodes;
+  CU(cudaMemcpyAsync(b.em, emission, eb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(b.trans, trans, tb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (first_node_id) *first_node_id = b.first;
+  return 0;
+}
+
+int dcpgpu_pool_release(dcpgpu_ctx *ctx)
+{
+  if (!ctx) return DCPGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (auto &b : ctx->pool)
+  {
+    cudaFree(b.em);
+    cudaFree(b.trans);
+  }
+  ctx->pool.clear(); // node ids keep growing so that stale ids stay invalid
+  return 0;
+}
+
+int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t first_node_id,
+                       float const *BMk, float const *null_emission, float const *bg_emission,
+                       int32_t *profile_index)
+{
+  if (!ctx || K < 1 || K > DCPGPU_MAX_CORE_SIZE || !BMk || !null_emission || !bg_emission)
+    return fail(ctx, DCPGPU_EINVAL, "profile_add: bad argument");
+  CU(cudaSetDevice(ctx->device));
+
+  // resolve pool node ids to device rows
+  std::vector<NodeRef> refs((size_t)K);
+  size_t hint = 0;
+  for (int k = 0; k < K; ++k)
+  {
+    int64_t const id = node_ids ? node_ids[k] : first_node_id + k;
+    PoolBlock const *blk = nullptr;
+    if (hint < ctx->pool.size() && id >= ctx->pool[hint].first && id < ctx->pool[hint].first + ctx->pool[hint].n)
+      blk = &ctx->pool[hint];
+    else
+      for (size_t i = 0; i < ctx->pool.size(); ++i)
+        if (id >= ctx->pool[i].first && id < ctx->pool[i].first + ctx->pool[i].n)
+        {
+          blk = &ctx->pool[i];
+          hint = i;
+          break;
+        }
+    if (!blk) return fail(ctx, DCPGPU_EINVAL, "profile_add: node id not in the pool");
+    refs[k].em = blk->em + (size_t)(id - blk->first) * NCODES;
+    refs[k].trans = blk->trans + (size_t)(id - blk->first) * 7;
+  }
+
+  ProfileDesc d;
+  d.K = K;
+  layout_shape(K, &d.Q, &d.W);
+  d.Kpad = 32 * d.W * d.Q;
+  void *pem = nullptr, *pcore = nullptr, *pnb = nullptr;
+  int rc;
+  if ((rc = arena_alloc(ctx, (size_t)NCODES * d.Kpad * sizeof(float), &pem))) return rc;
+  if ((rc = arena_alloc(ctx, (size_t)C_ROWS * d.Kpad * sizeof(float), &pcore))) return rc;
+  if ((rc = arena_alloc(ctx, (size_t)NCODES * sizeof(float2), &pnb))) return rc;
+  d.em = static_cast<float *>(pem);
+  d.core = static_cast<float *>(pcore);
+  d.nulbg = static_cast<float2 *>(pnb);
+
+  // staging: refs | BMk | null | bg
+  size_t const o_refs = 0;
+  size_t const o_bm = (o_refs + (size_t)K * sizeof(NodeRef) + 255) & ~size_t(255);
+  size_t const o_nul = (o_bm + (size_t)K * sizeof(float) + 255) & ~size_t(255);
+  size_t const o_bg = o_nul + (size_t)NCODES * sizeof(float);
+  size_t const total = o_bg + (size_t)NCODES * sizeof(float);
+  if ((rc = ensure(ctx, ctx->d_stage, ctx->d_stage_cap, total))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_stage + o_refs, refs.data(), (size_t)K * sizeof(NodeRef), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_stage + o_bm, BMk, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_stage + o_nul, null_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_stage + o_bg, bg_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+
+  NodeRef const *drefs = reinterpret_cast<NodeRef const *>(ctx->d_stage + o_refs);
+  int const VL = 32 * d.W;
+  dim3 const grid((d.Kpad + 127) / 128, NCODES);
+  pack_em_kernel<<<grid, 128, 0, ctx->stream>>>(drefs, K, d.Q, VL, d.Kpad, static_cast<float *>(pem));
+  pack_core_kernel<<<(d.Kpad + 127) / 128, 128, 0, ctx->stream>>>(
+      drefs, reinterpret_cast<float const *>(ctx->d_stage + o_bm), K, d.Q, VL, d.Kpad, static_cast<float *>(pcore));
+  pack_nulbg_kernel<<<(NCODES + 127) / 128, 128, 0, ctx->stream>>>(
+      reinterpret_cast<float const *>(ctx->d_stage + o_nul), reinterpret_cast<float const *>(ctx->d_stage + o_bg),
+      static_cast<float2 *>(pnb));
+  CU(cudaGetLastError());
+  // the staging buffer is reused by the next call: finish the pack first
+  CU(cudaStreamSynchronize(ctx->stream));
+
+  ctx->h_profiles.push_back(d);
+  ctx->profiles_dirty = true;
+  if (profile_index) *profile_index = (int32_t)ctx->h_profiles.size() - 1;
+  return 0;
+}
+
+int dcpgpu_profile_count(dcpgpu_ctx const *ctx) { return ctx ? (int)ctx->h_profiles.size() : 0; }
+
+int dcpgpu_profile_core_size(dcpgpu_ctx const *ctx, int32_t profile)
+{
+  if (!ctx || profile < 0 || (size_t)profile >= ctx->h_profiles.size()) return -1;
+  return ctx->h_profiles[(size_t)profile].K;
+}
+
+int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int64_t const *offsets)
+{
+  if (!ctx || nseq < 0 || (nseq > 0 && (!symbols || !offsets))) return fail(ctx, DCPGPU_EINVAL, "reads_set: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<long long> seq_word((size_t)nseq);
+  std::vector<int> seq_len((size_t)nseq);
+  long long nwords = 0;
+  int maxlen = 0;
+  for (int s = 0; s < nseq; ++s)
+  {
+    int64_t const len = offsets[s + 1] - offsets[s];
+    if (len < 0 || len > INT32_MAX) return fail(ctx, DCPGPU_EINVAL, "reads_set: bad offsets");
+    seq_word[s] = nwords;
+    seq_len[s] = (int)len;
+    nwords += (len + 15) / 16 + 1; // +1: the kernels prefetch one word past the end
+    maxlen = std::max(maxlen, (int)len);
+  }
+  std::vector<uint32_t> words((size_t)nwords + 1, 0u);
+  for (int s = 0; s < nseq; ++s)
+  {
+    uint8_t const *x = symbols + offsets[s];
+    uint32_t *w = words.data() + seq_word[s];
+    for (int i = 0; i < seq_len[s]; ++i)
+    {
+      if (x[i] > 3) return fail(ctx, DCPGPU_EINVAL, "reads_set: symbol outside 0..3");
+      w[i >> 4] |= (uint32_t)x[i] << (2 * (i & 15));
+    }
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->d_words) CU(cudaFree(ctx->d_words));
+  if (ctx->d_seq_word) CU(cudaFree(ctx->d_seq_word));
+  if (ctx->d_seq_len) CU(cudaFree(ctx->d_seq_len));
+  ctx->d_words = nullptr;
+  ctx->d_seq_word = nullptr;
+  ctx->d_seq_len = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_words), words.size() * sizeof(uint32_t)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_seq_word), std::max<size_t>(1, seq_word.size()) * sizeof(long long)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_seq_len), std::max<size_t>(1, seq_len.size()) * sizeof(int)));
+  CU(cudaMemcpyAsync(ctx->d_words, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (nseq)
+  {
+    CU(cudaMemcpyAsync(ctx->d_seq_word, seq_word.data(), seq_word.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_seq_len, seq_len.data(), seq_len.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->h_seq_len.swap(seq_len);
+  ctx->nseq = nseq;
+  ctx->maxlen = std::min(maxlen, DCPGPU_MAX_WINDOW);
+  return 0;
+}
+
+int dcpgpu_reads_count(dcpgpu_ctx const *ctx) { return ctx ? ctx->nseq : 0; }
+
+static int check_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs, int *maxlen)
+{
+  int ml = 1;
+  for (int64_t i = 0; i < npairs; ++i)
+  {
+    dcpgpu_pair const &p = pairs[i];
+    if (p.profile < 0 || (size_t)p.profile >= ctx->h_profiles.size() || p.seq < 0 || p.seq >= ctx->nseq ||
+        p.start < 0 || p.len < 1 || p.len > DCPGPU_MAX_WINDOW ||
+        (int64_t)p.start + p.len > ctx->h_seq_len[(size_t)p.seq])
+      return fail(ctx, DCPGPU_EINVAL, "pair out of range");
+    ml = std::max(ml, p.len);
+  }
+  *maxlen = ml;
+  return 0;
+}
+
+int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs, uint32_t flags,
+                       float *null_cost, float *alt_cost)
+{
+  if (!ctx || npairs < 0 || (npairs && !pairs)) return fail(ctx, DCPGPU_EINVAL, "score_pairs: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc, maxlen = 1;
+  if ((rc = check_pairs(ctx, npairs, pairs, &maxlen))) return rc;
+  if ((rc = ensure_xt(ctx, flags, maxlen))) return rc;
+  if ((rc = begin_pass(ctx, (size_t)npairs))) return rc;
+  if (npairs == 0) return end_pass(ctx, 0);
+
+  // bucket by kernel class, keeping the caller's order inside a class
+  std::vector<std::vector<long long>> bucket(MAXQ_REG + 1);
+  int maxK_generic = 1;
+  double cells = 0;
+  for (int64_t i = 0; i < npairs; ++i)
+  {
+    ProfileDesc const &d = ctx->h_profiles[(size_t)pairs[i].profile];
+    int const c = kernel_class(d);
+    bucket[(size_t)c].push_back(i);
+    if (c == 0) maxK_generic = std::max(maxK_generic, d.K);
+    cells += (double)pairs[i].len * d.K;
+  }
+  std::vector<long long> order;
+  order.reserve((size_t)npairs);
+  size_t first[MAXQ_REG + 2];
+  for (int c = 0; c <= MAXQ_REG; ++c)
+  {
+    first[c] = order.size();
+    order.insert(order.end(), bucket[(size_t)c].begin(), bucket[(size_t)c].end());
+  }
+  first[MAXQ_REG + 1] = order.size();
+
+  if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
+  if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+
+  for (int c = 0; c <= MAXQ_REG; ++c)
+  {
+    size_t const n = first[c + 1] - first[c];
+    if (!n) continue;
+    ScoreArgs a{};
+    a.profiles = ctx->d_profiles;
+    a.reads = reads_view(ctx);
+    a.xt = ctx->d_xt[flags & 3u];
+    a.pairs = ctx->d_pairs;
+    a.order = ctx->d_order + first[c];
+    a.nitems = n;
+    a.counter = ctx->d_counters + c;
+    a.out = ctx->d_out;
+    a.nhits = ctx->d_counters + 16;
+    if (c == 0)
+    {
+      GenArgs g{};
+      g.s = a;
+      if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
+    }
+    else if ((rc = launch_class(ctx, c, a)))
+      return rc;
+  }
+  ctx->last_cells = cells;
+  if ((rc = end_pass(ctx, npairs))) return rc;
+  return dcpgpu_scores_fetch(ctx, npairs, null_cost, alt_cost);
+}
+
+int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq0, int32_t seq1, uint32_t flags)
+{
+  if (!ctx || prof0 < 0 || prof1 < prof0 || (size_t)prof1 > ctx->h_profiles.size() || seq0 < 0 || seq1 < seq0 ||
+      seq1 > ctx->nseq)
+    return fail(ctx, DCPGPU_EINVAL, "score_grid: bad range");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  int const nprof = prof1 - prof0, nseq = seq1 - seq0;
+  size_t const npairs = (size_t)nprof * (size_t)nseq;
+  if ((rc = ensure_xt(ctx, flags, std::max(ctx->maxlen, 1)))) return rc;
+  if ((rc = begin_pass(ctx, npairs))) return rc;
+  if (npairs == 0) return end_pass(ctx, 0);
+
+  std::vector<std::vector<int>> bucket(MAXQ_REG + 1);
+  int maxK_generic = 1;
+  double cells = 0;
+  // cells = sum over pairs of min(50K, 100000, len) * K
+  std::vector<int> lens(ctx->h_seq_len.begin() + seq0, ctx->h_seq_len.begin() + seq1);
+  std::sort(lens.begin(), lens.end());
+  std::vector<double> prefix(lens.size() + 1, 0.0);
+  for (size_t i = 0; i < lens.size(); ++i) prefix[i + 1] = prefix[i] + lens[i];
+  for (int p = prof0; p < prof1; ++p)
+  {
+    ProfileDesc const &d = ctx->h_profiles[(size_t)p];
+    int const c = kernel_class(d);
+    bucket[(size_t)c].push_back(p);
+    if (c == 0) maxK_generic = std::max(maxK_generic, d.K);
+    int const w = std::min(d.K * 50, DCPGPU_MAX_WINDOW);
+    size_t const nle = std::upper_bound(lens.begin(), lens.end(), w) - lens.begin();
+    cells += (prefix[nle] + (double)(lens.size() - nle) * w) * d.K;
+  }
+  std::vector<int> flat;
+  flat.reserve((size_t)nprof);
+  size_t first[MAXQ_REG + 2];
+  for (int c = 0; c <= MAXQ_REG; ++c)
+  {
+    first[c] = flat.size();
+    flat.insert(flat.end(), bucket[(size_t)c].begin(), bucket[(size_t)c].end());
+  }
+  first[MAXQ_REG + 1] = flat.size();
+  if ((rc = ensure(ctx, ctx->d_class_profiles, ctx->class_profiles_cap, flat.size()))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+
+  // large classes first: the generic kernel (big K) has the longest tail
+  for (int c = 0; c <= MAXQ_REG; ++c)
+  {
+    size_t const n = first[c + 1] - first[c];
+    if (!n) continue;
+    ScoreArgs a{};
+    a.profiles = ctx->d_profiles;
+    a.reads = reads_view(ctx);
+    a.xt = ctx->d_xt[flags & 3u];
+    a.class_profiles = ctx->d_class_profiles + first[c];
+    a.prof0 = prof0;
+    a.seq0 = seq0;
+    a.nseq = nseq;
+    a.nitems = (unsigned long long)n * (unsigned long long)nseq;
+    a.counter = ctx->d_counters + c;
+    a.out = ctx->d_out;
+    a.nhits = ctx->d_counters + 16;
+    if (c == 0)
+    {
+      GenArgs g{};
+      g.s = a;
+      if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
+    }
+    else if ((rc = launch_class(ctx, c, a)))
+      return rc;
+  }
+  ctx->last_cells = cells;
+  return end_pass(ctx, (int64_t)npairs);
+}
+
+int dcpgpu_scores_fetch(dcpgpu_ctx *ctx, int64_t npairs, float *null_cost, float *alt_cost)
+{
+  if (!ctx || npairs < 0 || npairs > ctx->last_n) return fail(ctx, DCPGPU_EINVAL, "scores_fetch: bad count");
+  CU(cudaSetDevice(ctx->device));
+  if (npairs && (null_cost || alt_cost))
+  {
+    std::vector<float2> h((size_t)npairs);
+    CU(cudaMemcpyAsync(h.data(), ctx->d_out, (size_t)npairs * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < npairs; ++i)
+    {
+      if (null_cost) null_cost[i] = h[(size_t)i].x;
+      if (alt_cost) alt_cost[i] = h[(size_t)i].y;
+    }
+  }
+  else
+    CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t *nhits)
+{
+  if (!ctx || cap < 0 || !nhits) return fail(ctx, DCPGPU_EINVAL, "hits_fetch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  unsigned long long n = 0;
+  CU(cudaMemcpyAsync(&n, ctx->d_counters + 16, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *nhits = (int64_t)n;
+  if (!hit_index || cap == 0 || n == 0) return 0;
+  long long *d_idx = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&d_idx), (size_t)n * sizeof(long long)));
+  CU(cudaMemsetAsync(ctx->d_counters + 17, 0, sizeof(unsigned long long), ctx->stream));
+  long long const N = ctx->last_n;
+  hits_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, N, ctx->d_counters + 17,
+                                                                       (long long)n, d_idx);
+  std::vector<long long> h((size_t)n);
+  cudaError_t e = cudaMemcpyAsync(h.data(), d_idx, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_idx);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "hits_fetch");
+  std::sort(h.begin(), h.end());
+  for (int64_t i = 0; i < std::min<int64_t>(cap, (int64_t)n); ++i)
+    hit_index[i] = h[(size_t)i];
+  return 0;
+}
+
+double dcpgpu_last_cells(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_cells : 0.0; }
+int64_t dcpgpu_last_launches(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_launches : 0; }
+
+float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx)
+{
+  if (!ctx || !ctx->timed) return -1.0f;
+  cudaSetDevice(ctx->device);
+  if (cudaEventSynchronize(ctx->ev1) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs, uint32_t flags,
+                       float *alt_cost, int32_t *nsteps)
+{
+  if (!ctx || npairs < 0 || (npairs && !pairs)) return fail(ctx, DCPGPU_EINVAL, "trace_pairs: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int rc, maxlen = 1;
+  ctx->traced = false;
+  if ((rc = check_pairs(ctx, npairs, pairs, &maxlen))) return rc;
+  if ((rc = ensure_xt(ctx, flags, maxlen))) return rc;
+  if ((rc = sync_profiles(ctx))) return rc;
+  ctx->t_pairs.assign(reinterpret_cast<Pair const *>(pairs), reinterpret_cast<Pair const *>(pairs) + npairs);
+  ctx->t_xnode_off.assign((size_t)npairs + 1, 0);
+  ctx->t_node_off.assign((size_t)npairs + 1, 0);
+  ctx->t_nsteps.assign((size_t)npairs, 0);
+  if (npairs == 0)
+  {
+    ctx->traced = true;
+    return 0;
+  }
+  int maxK = 1;
+  for (int64_t i = 0; i < npairs; ++i)
+  {
+    int const K = ctx->h_profiles[(size_t)pairs[i].profile].K;
+    maxK = std::max(maxK, K);
+    ctx->t_xnode_off[(size_t)i + 1] = ctx->t_xnode_off[(size_t)i] + (pairs[i].len + 1);
+    ctx->t_node_off[(size_t)i + 1] = ctx->t_node_off[(size_t)i] + (long long)(pairs[i].len + 1) * K;
+  }
+  cudaFree(ctx->d_tpairs); ctx->d_tpairs = nullptr;
+  cudaFree(ctx->d_xnodes); ctx->d_xnodes = nullptr;
+  cudaFree(ctx->d_nodes); ctx->d_nodes = nullptr;
+  cudaFree(ctx->d_xnode_off); ctx->d_xnode_off = nullptr;
+  cudaFree(ctx->d_node_off); ctx->d_node_off = nullptr;
+  cudaFree(ctx->d_nsteps); ctx->d_nsteps = nullptr;
+  cudaFree(ctx->d_tout); ctx->d_tout = nullptr;
+  size_t const n = (size_t)npairs;
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tpairs), n * sizeof(Pair)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xnodes), (size_t)ctx->t_xnode_off[n] * sizeof(uint32_t)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_nodes), (size_t)ctx->t_node_off[n] * sizeof(uint16_t)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xnode_off), (n + 1) * sizeof(long long)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_node_off), (n + 1) * sizeof(long long)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_nsteps), n * sizeof(int)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tout), n * sizeof(float2)));
+  CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + 18, 0, 2 * sizeof(unsigned long long), ctx->stream));
+
+  GenArgs g{};
+  g.s.profiles = ctx->d_profiles;
+  g.s.reads = reads_view(ctx);
+  g.s.xt = ctx->d_xt[flags & 3u];
+  g.s.pairs = ctx->d_tpairs;
+  g.s.order = nullptr;
+  g.s.nitems = n;
+  g.s.counter = ctx->d_counters + 18;
+  g.s.out = ctx->d_tout;
+  g.s.nhits = ctx->d_counters + 19;
+  g.xnodes = ctx->d_xnodes;
+  g.nodes = ctx->d_nodes;
+  g.xnode_off = ctx->d_xnode_off;
+  g.node_off = ctx->d_node_off;
+  g.nsteps = ctx->d_nsteps;
+  if ((rc = launch_generic<true>(ctx, g, maxK))) return rc;
+
+  std::vector<float2> h(n);
+  CU(cudaMemcpyAsync(h.data(), ctx->d_tout, n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (size_t i = 0; i < n; ++i)
+  {
+    if (alt_cost) alt_cost[i] = h[i].y;
+    if (nsteps) nsteps[i] = ctx->t_nsteps[i];
+    if (ctx->t_nsteps[i] <= 0) return fail(ctx, DCPGPU_ESTATE, "trace: corrupt trellis (internal error)");
+  }
+  ctx->traced = true;
+  return 0;
+}
+
+int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_ids, uint8_t *seqsizes)
+{
+  if (!ctx || !ctx->traced) return fail(ctx, DCPGPU_ESTATE, "trace_fetch before trace_pairs");
+  size_t const n = ctx->t_pairs.size();
+  if (n == 0) return 0;
+  if (!offsets || !state_ids || !seqsizes) return fail(ctx, DCPGPU_EINVAL, "trace_fetch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  // device-side compact layout; the caller's offsets may be any non-overlapping placement
+  std::vector<long long> off(n + 1, 0);
+  for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + ctx->t_nsteps[i];
+  size_t const total = (size_t)off[n];
+  uint16_t *d_ids = nullptr;
+  uint8_t *d_sz = nullptr;
+  cudaFree(ctx->d_step_off); ctx->d_step_off = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_step_off), (n + 1) * sizeof(long long)));
+  CU(cudaMalloc(reinterpret_cast<void **>(&d_ids), total * sizeof(uint16_t)));
+  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_sz), total);
+  if (e != cudaSuccess) { cudaFree(d_ids); return fail_cuda(ctx, e, "cudaMalloc(steps)"); }
+  std::vector<uint16_t> h_ids(total);
+  std::vector<uint8_t> h_sz(total);
+  e = cudaMemcpyAsync(ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess)
+  {
+    WalkArgs w{};
+    w.profiles = ctx->d_profiles;
+    w.pairs = ctx->d_tpairs;
+    w.npairs = (long long)n;
+    w.xnodes = ctx->d_xnodes;
+    w.nodes = ctx->d_nodes;
+    w.xnode_off = ctx->d_xnode_off;
+    w.node_off = ctx->d_node_off;
+    w.nsteps = ctx->d_nsteps;
+    w.step_off = ctx->d_step_off;
+    w.ids = d_ids;
+    w.sizes = d_sz;
+    walk_write_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(w);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_ids);
+  cudaFree(d_sz);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "trace_fetch");
+  for (size_t i = 0; i < n; ++i)
+  {
+    std::memcpy(state_ids + offsets[i], h_ids.data() + off[i], (size_t)ctx->t_nsteps[i] * sizeof(uint16_t));
+    std::memcpy(seqsizes + offsets[i], h_sz.data() + off[i], (size_t)ctx->t_nsteps[i]);
+  }
+  return 0;
+}
+
+int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t *nodes)
+{
+  if (!ctx || !ctx->traced) return fail(ctx, DCPGPU_ESTATE, "trace_trellis before trace_pairs");
+  if (i < 0 || (size_t)i >= ctx->t_pairs.size()) return fail(ctx, DCPGPU_EINVAL, "trace_trellis: bad index");
+  CU(cudaSetDevice(ctx->device));
+  size_t const nx = (size_t)(ctx->t_xnode_off[(size_t)i + 1] - ctx->t_xnode_off[(size_t)i]);
+  size_t const nn = (size_t)(ctx->t_node_off[(size_t)i + 1] - ctx->t_node_off[(size_t)i]);
+  if (xnodes)
+    CU(cudaMemcpyAsync(xnodes, ctx->d_xnodes + ctx->t_xnode_off[(size_t)i], nx * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  if (nodes)
+    CU(cudaMemcpyAsync(nodes, ctx->d_nodes + ctx->t_node_off[(size_t)i], nn * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int dcpgpu_xtrans(int window_len, uint32_t flags, float out[13])
+{
+  if (window_len < 1 || !out) return DCPGPU_EINVAL;
+  float tmp[X_STRIDE];
+  host_xtrans(window_len, flags & DCPGPU_MULTI_HITS, flags & DCPGPU_HMMER3_COMPAT, tmp);
+  std::memcpy(out, tmp, 13 * sizeof(float));
+  return 0;
+}
+
+} // extern "C"

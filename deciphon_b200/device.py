@@ -1,0 +1,205 @@
+"""Host-side handle of one B200: resident profiles + packed reads + score/trace passes.
+
+Thin object layer over the C ABI (include/dcpgpu.h).  It plays the role of the reference's
+per-thread ``work``/``viterbi`` objects (c-core/work.c:24-51, thread.c:98-128), but for a
+whole batch of (window, profile) pairs at once.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import HMMER3_COMPAT, MULTI_HITS, DcpGpuError, lib
+
+PAIR_DTYPE = np.dtype([("profile", "<i4"), ("seq", "<i4"), ("start", "<i4"), ("len", "<i4")])
+
+
+def flags_of(multi_hits: bool, hmmer3_compat: bool) -> int:
+    return (MULTI_HITS if multi_hits else 0) | (HMMER3_COMPAT if hmmer3_compat else 0)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Device:
+    def __init__(self, index: int = 0):
+        h = C.c_void_p()
+        rc = lib.dcpgpu_open(C.byref(h), index)
+        if rc:
+            raise DcpGpuError(rc, lib.dcpgpu_strerror(rc).decode())
+        self._h = h
+        self.index = index
+
+    # -- plumbing ------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc:
+            detail = lib.dcpgpu_last_error(self._h).decode()
+            raise DcpGpuError(rc, f"{lib.dcpgpu_strerror(rc).decode()} ({detail})")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.dcpgpu_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(lib.dcpgpu_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def sync(self):
+        self._check(lib.dcpgpu_sync(self._h))
+
+    @property
+    def sm_count(self) -> int:
+        return int(lib.dcpgpu_device_info(self._h, 0))
+
+    @property
+    def profile_bytes(self) -> int:
+        return int(lib.dcpgpu_device_info(self._h, 3))
+
+    def free_bytes(self) -> int:
+        return int(lib.dcpgpu_device_info(self._h, 2))
+
+    # -- profiles ------------------------------------------------------------------------
+    def pool_add(self, emission: np.ndarray, trans: np.ndarray) -> int:
+        """Upload nodes in .dcp (log-prob) form; returns the id of the first one."""
+        emission = np.ascontiguousarray(emission, dtype=np.float32)
+        trans = np.ascontiguousarray(trans, dtype=np.float32)
+        n = emission.shape[0]
+        assert emission.shape == (n, 1364) and trans.shape == (n, 7)
+        first = C.c_int64()
+        self._check(lib.dcpgpu_pool_add(self._h, n, _ptr(emission), _ptr(trans), C.byref(first)))
+        return first.value
+
+    def pool_release(self):
+        self._check(lib.dcpgpu_pool_release(self._h))
+
+    def profile_add(self, K: int, BMk, null_emission, bg_emission, node_ids=None, first_node_id: int = 0) -> int:
+        BMk = np.ascontiguousarray(BMk, dtype=np.float32)
+        nul = np.ascontiguousarray(null_emission, dtype=np.float32)
+        bg = np.ascontiguousarray(bg_emission, dtype=np.float32)
+        ids = None if node_ids is None else np.ascontiguousarray(node_ids, dtype=np.int64)
+        assert BMk.size == K and nul.size == 1364 and bg.size == 1364
+        assert ids is None or ids.size == K
+        idx = C.c_int32()
+        self._check(lib.dcpgpu_profile_add(self._h, K, _ptr(ids), first_node_id, _ptr(BMk), _ptr(nul), _ptr(bg),
+                                           C.byref(idx)))
+        return idx.value
+
+    def add_profile(self, prof) -> int:
+        """Make a ``dcp_file.Profile`` resident (the GPU analogue of work_setup, work.c:24-46)."""
+        K = prof.core_size
+        first = self.pool_add(prof.emission[:K], prof.trans[:K])
+        idx = self.profile_add(K, prof.BMk, prof.null_emission, prof.bg_emission, None, first)
+        self.pool_release()
+        return idx
+
+    @property
+    def num_profiles(self) -> int:
+        return lib.dcpgpu_profile_count(self._h)
+
+    def core_size(self, profile: int) -> int:
+        return lib.dcpgpu_profile_core_size(self._h, profile)
+
+    # -- reads ---------------------------------------------------------------------------
+    def set_reads(self, reads):
+        """reads: list of uint8 arrays of symbols 0..3 (A,C,G,T/U)."""
+        off = np.zeros(len(reads) + 1, dtype=np.int64)
+        if len(reads):
+            off[1:] = np.cumsum([len(r) for r in reads])
+            sym = np.ascontiguousarray(np.concatenate(reads), dtype=np.uint8)
+        else:
+            sym = np.zeros(1, dtype=np.uint8)
+        self._check(lib.dcpgpu_reads_set(self._h, len(reads), _ptr(sym), _ptr(off)))
+
+    def set_reads_packed(self, symbols: np.ndarray, offsets: np.ndarray):
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self._check(lib.dcpgpu_reads_set(self._h, len(offsets) - 1, _ptr(symbols), _ptr(offsets)))
+
+    # -- score pass ----------------------------------------------------------------------
+    def score_pairs(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):
+        """pairs: structured array of PAIR_DTYPE (or int32[n,4]).  Returns (null_cost, alt_cost)."""
+        pairs = np.ascontiguousarray(pairs)
+        if pairs.dtype != PAIR_DTYPE:
+            pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4).view(PAIR_DTYPE).reshape(-1)
+        n = pairs.shape[0]
+        nul = np.empty(n, dtype=np.float32)
+        alt = np.empty(n, dtype=np.float32)
+        self._check(lib.dcpgpu_score_pairs(self._h, n, _ptr(pairs), flags_of(multi_hits, hmmer3_compat),
+                                           _ptr(nul), _ptr(alt)))
+        return nul, alt
+
+    def score_grid(self, prof0: int, prof1: int, seq0: int, seq1: int, multi_hits=True, hmmer3_compat=False):
+        """Asynchronous: first window of every seq in [seq0,seq1) x every profile in [prof0,prof1)."""
+        self._check(lib.dcpgpu_score_grid(self._h, prof0, prof1, seq0, seq1, flags_of(multi_hits, hmmer3_compat)))
+
+    def scores_fetch(self, n: int):
+        nul = np.empty(n, dtype=np.float32)
+        alt = np.empty(n, dtype=np.float32)
+        self._check(lib.dcpgpu_scores_fetch(self._h, n, _ptr(nul), _ptr(alt)))
+        return nul, alt
+
+    def hits_fetch(self) -> np.ndarray:
+        n = C.c_int64()
+        self._check(lib.dcpgpu_hits_fetch(self._h, 0, None, C.byref(n)))
+        idx = np.empty(n.value, dtype=np.int64)
+        if n.value:
+            self._check(lib.dcpgpu_hits_fetch(self._h, n.value, _ptr(idx), C.byref(n)))
+        return idx
+
+    def last_cells(self) -> float:
+        return float(lib.dcpgpu_last_cells(self._h))
+
+    def last_kernel_ms(self) -> float:
+        return float(lib.dcpgpu_last_kernel_ms(self._h))
+
+    def last_launches(self) -> int:
+        return int(lib.dcpgpu_last_launches(self._h))
+
+    # -- trace pass ----------------------------------------------------------------------
+    def trace_pairs(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):
+        """Returns (alt_cost[n], paths) with paths[i] = (state_ids uint16[], seqsizes uint8[])."""
+        pairs = np.ascontiguousarray(pairs)
+        if pairs.dtype != PAIR_DTYPE:
+            pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4).view(PAIR_DTYPE).reshape(-1)
+        n = pairs.shape[0]
+        alt = np.empty(n, dtype=np.float32)
+        nsteps = np.zeros(n, dtype=np.int32)
+        self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs), flags_of(multi_hits, hmmer3_compat),
+                                           _ptr(alt), _ptr(nsteps)))
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(nsteps)
+        ids = np.zeros(max(int(off[-1]), 1), dtype=np.uint16)
+        sz = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        self._check(lib.dcpgpu_trace_fetch(self._h, _ptr(off), _ptr(ids), _ptr(sz)))
+        paths = [(ids[off[i]:off[i + 1]].copy(), sz[off[i]:off[i + 1]].copy()) for i in range(n)]
+        return alt, paths
+
+    def trace_trellis(self, i: int, length: int, K: int):
+        xn = np.zeros(length + 1, dtype=np.uint32)
+        nd = np.zeros((length + 1) * K, dtype=np.uint16)
+        self._check(lib.dcpgpu_trace_trellis(self._h, i, _ptr(xn), _ptr(nd)))
+        return xn, nd
+
+
+def xtrans(window_len: int, multi_hits=True, hmmer3_compat=False) -> np.ndarray:
+    """The 13 special-transition costs the device uses for a window (host computation)."""
+    out = np.zeros(13, dtype=np.float32)
+    rc = lib.dcpgpu_xtrans(window_len, flags_of(multi_hits, hmmer3_compat), _ptr(out))
+    if rc:
+        raise DcpGpuError(rc, lib.dcpgpu_strerror(rc).decode())
+    return out

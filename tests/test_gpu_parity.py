@@ -1,0 +1,186 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the
+C ABI, against the oracle, the committed reference-generated vectors and -- when the
+prebuilt oracle/_ref travelled with the snapshot -- the reference's own compiled code.
+Integer/index work and fp32 scores are compared BIT-EXACT (stronger than the 1e-4 absolute
+log-likelihood tolerance of the north star)."""
+import numpy as np
+import pytest
+
+from deciphon_b200 import synth
+from deciphon_b200.device import PAIR_DTYPE
+
+pytestmark = pytest.mark.gpu
+
+FLAGS = [(False, False), (True, False), (False, True), (True, True)]  # index f: mh = f&1, h3 = f&2
+
+
+def _pairs(rows):
+    return np.asarray(rows, dtype=np.int32).reshape(-1, 4).view(PAIR_DTYPE).reshape(-1)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def golden_dev(device, golden_profiles, ref_vectors):
+    """3 golden profiles + the 50 reads of ref_vectors.npz resident on the device."""
+    base = device.num_profiles
+    for p in golden_profiles:
+        device.add_profile(p)
+    off, sym = ref_vectors["offsets"], ref_vectors["symbols"]
+    reads = [np.ascontiguousarray(sym[off[i]:off[i + 1]]) for i in range(len(off) - 1)]
+    device.set_reads(reads)
+    return base, reads
+
+
+def test_score_matches_reference_vectors(device, golden_dev, ref_vectors):
+    """viterbi_null + viterbi_cost of the reference, 600 (read, profile) pairs x 4 flag combos."""
+    base, reads = golden_dev
+    rows = [(base + pi, ri, 0, len(reads[ri])) for pi in range(3) for ri in range(len(reads))]
+    for f in range(4):
+        nul, alt = device.score_pairs(_pairs(rows), bool(f & 1), bool(f & 2))
+        want_n = ref_vectors["null_cost"][f].reshape(-1)
+        want_a = ref_vectors["alt_cost"][f].reshape(-1)
+        assert np.array_equal(_bits(nul), _bits(want_n))
+        assert np.array_equal(_bits(alt), _bits(want_a))
+
+
+def test_golden_lrt(device, golden_dev, golden_reads, oracle):
+    """The reference's golden snap.dcs rows: LRT 291.6 / 349.3 / 360.4."""
+    base, reads = golden_dev
+    from oracle.oracle import encode
+    cons = [encode(r["data"]) for r in golden_reads["consensus_fna"]]
+    device.set_reads(cons)
+    nul, alt = device.score_pairs(_pairs([(base + i, i, 0, len(cons[i])) for i in range(3)]))
+    assert ["%.1f" % oracle.lrt(n, a) for n, a in zip(nul, alt)] == ["291.6", "349.3", "360.4"]
+    device.set_reads(reads)
+
+
+def test_grid_equals_pairs_and_hits(device, golden_dev, ref_vectors, oracle):
+    base, reads = golden_dev
+    n = len(reads)
+    device.score_grid(base, base + 3, 0, n, True, False)
+    nul, alt = device.scores_fetch(3 * n)
+    assert np.array_equal(_bits(nul), _bits(ref_vectors["null_cost"][1].reshape(-1)))
+    assert np.array_equal(_bits(alt), _bits(ref_vectors["alt_cost"][1].reshape(-1)))
+    hits = device.hits_fetch()
+    lrt = np.array([oracle.lrt(a, b) for a, b in zip(nul, alt)])
+    want = np.nonzero(np.isfinite(lrt) & (lrt >= 0))[0]
+    assert np.array_equal(hits, want)
+    key = ref_vectors["path_key"]
+    assert len(want) == int((key[:, 0] == 1).sum())
+    assert device.last_cells() == float(sum(len(r) for r in reads) * sum(device.core_size(base + i) for i in range(3)))
+
+
+def test_trace_matches_reference_paths(device, golden_dev, ref_vectors):
+    """viterbi_path + trellis_unzip of the reference: every step of the 130 hit paths."""
+    base, reads = golden_dev
+    key = ref_vectors["path_key"]
+    at = 0
+    starts = np.concatenate([[0], np.cumsum(key[:, 3])])
+    for f in range(4):
+        sel = np.nonzero(key[:, 0] == f)[0]
+        rows = [(base + key[i, 1], key[i, 2], 0, len(reads[key[i, 2]])) for i in sel]
+        alt, paths = device.trace_pairs(_pairs(rows), bool(f & 1), bool(f & 2))
+        for j, i in enumerate(sel):
+            ids, sz = paths[j]
+            assert np.array_equal(ids, ref_vectors["path_ids"][starts[i]:starts[i + 1]]), (f, i)
+            assert np.array_equal(sz, ref_vectors["path_sizes"][starts[i]:starts[i + 1]]), (f, i)
+            assert _bits(alt[j:j + 1])[0] == _bits(ref_vectors["alt_cost"][f, key[i, 1], key[i, 2]].reshape(1))[0]
+            at += 1
+    assert at == len(key)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 31, 32, 33, 64, 97, 128, 160, 161, 200, 224, 225, 255, 256, 257, 300, 520, 1100])
+def test_score_and_trace_synthetic_K(device, oracle, node_pool, K):
+    """Every kernel class (Q = 1..8 register kernels and the generic kernel) against the oracle:
+    scores bit-exact, trellis words bit-exact, paths identical; unaligned window starts."""
+    rng = np.random.default_rng(1000 + K)
+    ids = rng.integers(0, len(node_pool), size=K)
+    prof = synth.synth_profile(rng, K, node_pool)
+    ids = None
+    costs = prof.costs()
+    p = device.add_profile(prof)
+    cons = np.stack([np.argmax(prof.emission[:K, 20:84], axis=1) // 16,
+                     (np.argmax(prof.emission[:K, 20:84], axis=1) // 4) % 4,
+                     np.argmax(prof.emission[:K, 20:84], axis=1) % 4], axis=1).reshape(-1).astype(np.uint8)
+    reads = []
+    for t in range(6):
+        if t < 3:
+            x = np.concatenate([synth.random_read(rng, 5 + 7 * t), synth.mutate(rng, cons, 0.05 * t), synth.random_read(rng, 3 + t)])
+            if t == 2:
+                x = np.concatenate([x, synth.mutate(rng, cons, 0.1)])  # two domains -> J state
+        else:
+            x = synth.random_read(rng, int(rng.integers(1, 300)))
+        reads.append(np.ascontiguousarray(x[:3000]))
+    device.set_reads(reads)
+    rows = []
+    for ri, x in enumerate(reads):
+        rows.append((p, ri, 0, len(x)))
+        if len(x) > 40:  # a window that starts mid-word and ends before the read does
+            rows.append((p, ri, 17, len(x) - 17 - 5))
+            rows.append((p, ri, 1, min(len(x) - 1, 33)))
+    for f in (1, 2):
+        mh, h3 = bool(f & 1), bool(f & 2)
+        nul, alt = device.score_pairs(_pairs(rows), mh, h3)
+        hit_rows = []
+        for j, (_, ri, st, ln) in enumerate(rows):
+            x = np.ascontiguousarray(reads[ri][st:st + ln])
+            xt = oracle.xtrans(ln, mh, h3)
+            assert _bits(nul[j:j + 1])[0] == _bits(oracle.null(costs[0], xt, x).reshape(1))[0], (K, j, "null")
+            assert _bits(alt[j:j + 1])[0] == _bits(oracle.alt(costs, xt, x).reshape(1))[0], (K, j, "alt")
+            lrt = oracle.lrt(nul[j], alt[j])
+            if np.isfinite(lrt) and lrt >= 0:
+                hit_rows.append(rows[j])
+        hit_rows = hit_rows[:4] + rows[-1:]  # also trace a non-hit: the trellis must still match
+        talt, paths = device.trace_pairs(_pairs(hit_rows), mh, h3)
+        for j, (_, ri, st, ln) in enumerate(hit_rows):
+            x = np.ascontiguousarray(reads[ri][st:st + ln])
+            xt = oracle.xtrans(ln, mh, h3)
+            oalt, oxn, ond = oracle.trace(costs, xt, x)
+            assert _bits(talt[j:j + 1])[0] == _bits(oalt.reshape(1))[0]
+            gxn, gnd = device.trace_trellis(j, ln, K)
+            assert np.array_equal(gxn, oxn), (K, j, "xnodes")
+            assert np.array_equal(gnd, ond), (K, j, "nodes")
+            oids, osz = oracle.unzip(K, ln, oxn, ond)
+            assert np.array_equal(paths[j][0], oids) and np.array_equal(paths[j][1], osz)
+            assert int(paths[j][1].sum()) == ln
+
+
+def test_against_compiled_reference(device, reference, oracle, node_pool):
+    """Same inputs through the reference's own viterbi.c/trellis.c (oracle/_ref, prebuilt)."""
+    rng = np.random.default_rng(99)
+    for K in (40, 200, 300):
+        prof = synth.synth_profile(rng, K, node_pool)
+        costs = prof.costs()
+        p = device.add_profile(prof)
+        rp = reference.profile(costs)
+        cons = np.argmax(prof.emission[:K, 20:84], axis=1)
+        cons = np.stack([cons // 16, (cons // 4) % 4, cons % 4], axis=1).reshape(-1).astype(np.uint8)
+        reads = [synth.mutate(rng, np.concatenate([synth.random_read(rng, 30), cons, synth.random_read(rng, 30)]), r)
+                 for r in (0.0, 0.1, 0.2)] + [synth.random_read(rng, 500)]
+        device.set_reads(reads)
+        rows = [(p, i, 0, len(x)) for i, x in enumerate(reads)]
+        nul, alt = device.score_pairs(_pairs(rows), True, False)
+        talt, paths = device.trace_pairs(_pairs(rows[:3]), True, False)
+        for i, x in enumerate(reads):
+            rp.set_xtrans(oracle.xtrans(len(x), True, False))
+            assert _bits(nul[i:i + 1])[0] == _bits(rp.null(x).reshape(1))[0]
+            assert _bits(alt[i:i + 1])[0] == _bits(rp.cost(x).reshape(1))[0]
+            if i < 3:
+                rids, rsz = rp.path(x)
+                assert np.array_equal(paths[i][0], rids) and np.array_equal(paths[i][1], rsz)
+
+
+def test_empty_and_invalid(device, golden_dev):
+    base, reads = golden_dev
+    from deciphon_b200.device import DcpGpuError
+    nul, alt = device.score_pairs(_pairs([]))
+    assert len(nul) == 0 and len(alt) == 0
+    with pytest.raises(DcpGpuError):
+        device.score_pairs(_pairs([(base, 0, 0, len(reads[0]) + 1)]))  # window past the read end
+    with pytest.raises(DcpGpuError):
+        device.score_pairs(_pairs([(10 ** 6, 0, 0, 1)]))
+    with pytest.raises(DcpGpuError):
+        device.score_pairs(_pairs([(base, 0, 0, 0)]))  # empty window (window.c BUG_ON)
