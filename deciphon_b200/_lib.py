@@ -35,7 +35,8 @@ SYMBOLS = [
     ("dcpgpu_hits_fetch", C.c_int, [_vp, _i64, _vp, C.POINTER(_i64)]),
     ("dcpgpu_last_cells", C.c_double, [_vp]),
     ("dcpgpu_last_kernel_ms", _f32, [_vp]),
-    ("dcpgpu_last_launches", _i64, [_vp]),
+    ("dcpgpu_launch_count", _i64, [_vp]),
+    ("dcpgpu_alu_peak", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     ("dcpgpu_trace_pairs", C.c_int, [_vp, _i64, _vp, _u32, _vp, _vp]),
     ("dcpgpu_trace_fetch", C.c_int, [_vp, _vp, _vp, _vp]),
     ("dcpgpu_trace_trellis", C.c_int, [_vp, _i64, _vp, _vp]),

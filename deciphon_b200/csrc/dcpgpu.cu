@@ -61,6 +61,7 @@ struct dcpgpu_ctx
   int64_t pool_nodes = 0;
 
   std::vector<ProfileDesc> h_profiles;
+  std::vector<char> h_unsafe; // a cost is negative/NaN: only the generic kernel may run it
   ProfileDesc *d_profiles = nullptr;
   size_t d_profiles_cap = 0;
   bool profiles_dirty = false;
@@ -97,7 +98,7 @@ struct dcpgpu_ctx
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   double last_cells = 0;
-  int64_t last_launches = 0;
+  int64_t launches = 0; // cumulative count of kernels this library launched
 
   // trace pass state
   std::vector<Pair> t_pairs;
@@ -170,7 +171,7 @@ int arena_alloc(dcpgpu_ctx *ctx, size_t bytes, void **out)
 
 // ---- pack kernels: .dcp log-probs -> cost-form device layout (protein.c:353-394) -------
 
-__global__ void pack_em_kernel(NodeRef const *nodes, int K, int Q, int VL, int Kpad, float *em)
+__global__ void pack_em_kernel(NodeRef const *nodes, int K, int Q, int VL, int Kpad, float *em, int *bad)
 {
   // x: node index over Kpad, y: code
   int const k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -178,11 +179,12 @@ __global__ void pack_em_kernel(NodeRef const *nodes, int K, int Q, int VL, int K
   if (k >= Kpad) return;
   float v = CUDART_INF_F;
   if (k < K) v = -nodes[k].em[code]; // viterbi_set_match(v, -emission[i], k, i), protein.c:390-391
+  if (!(v >= 0.0f)) atomicOr(bad, 1);  // negative or NaN cost: the register kernels' unsigned-order tricks do not apply
   em[(size_t)code * Kpad + layout_pos(k, Q, VL)] = v;
 }
 
 __global__ void pack_core_kernel(NodeRef const *nodes, float const *BMk, int K, int Q, int VL, int Kpad,
-                                 float *core)
+                                 float *core, int *bad)
 {
   int const k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
@@ -212,13 +214,19 @@ __global__ void pack_core_kernel(NodeRef const *nodes, float const *BMk, int K, 
   int const pos = layout_pos(k, Q, VL);
 #pragma unroll
   for (int i = 0; i < C_ROWS; ++i)
+  {
+    if (!(v[i] >= 0.0f)) atomicOr(bad, 1);
     core[(size_t)i * Kpad + pos] = v[i];
+  }
 }
 
-__global__ void pack_nulbg_kernel(float const *nul, float const *bg, float2 *out)
+__global__ void pack_nulbg_kernel(float const *nul, float const *bg, float2 *out, int *bad)
 {
   int const c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < NCODES) out[c] = make_float2(-nul[c], -bg[c]); // protein.c:387-388
+  if (c >= NCODES) return;
+  float2 const v = make_float2(-nul[c], -bg[c]); // protein.c:387-388
+  if (!(v.x >= 0.0f) || !(v.y >= 0.0f)) atomicOr(bad, 1);
+  out[c] = v;
 }
 
 __global__ void hits_fill_kernel(float2 const *out, long long n, unsigned long long *cursor,
@@ -308,19 +316,34 @@ int sync_profiles(dcpgpu_ctx *ctx)
   return 0;
 }
 
-int kernel_class(ProfileDesc const &p) { return (p.W == 1 && p.Q <= MAXQ_REG) ? p.Q : 0; }
+// Kernel classes: 0 = generic kernel; 1..8 = one warp per pair, Q nodes per lane;
+// 9..20 = W = 2/4/8 warps per pair, Q = 5..8.
+constexpr int NCLASS = 21;
 
-template <int Q>
+int kernel_class(dcpgpu_ctx const *ctx, int profile)
+{
+  ProfileDesc const &p = ctx->h_profiles[(size_t)profile];
+  if (ctx->h_unsafe[(size_t)profile] || p.Q > MAXQ_REG) return 0;
+  if (p.W == 1) return p.Q;
+  if (p.Q < 5) return 0;
+  if (p.W == 2) return 9 + (p.Q - 5);
+  if (p.W == 4) return 13 + (p.Q - 5);
+  if (p.W == 8) return 17 + (p.Q - 5);
+  return 0;
+}
+
+template <int Q, int W>
 int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
 {
+  constexpr int T = ScoreCfg<W>::THREADS, G = ScoreCfg<W>::GROUPS;
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q>, SCORE_THREADS, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W>, T, 0));
   if (per_sm < 1) per_sm = 1;
-  unsigned long long const want = (a.nitems + (SCORE_THREADS / 32) - 1) / (SCORE_THREADS / 32);
+  unsigned long long const want = (a.nitems + G - 1) / G;
   unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  score_reg_kernel<Q><<<grid, SCORE_THREADS, 0, ctx->stream>>>(a);
+  score_reg_kernel<Q, W><<<grid, T, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
-  ctx->last_launches += 1;
+  ctx->launches += 1;
   return 0;
 }
 
@@ -328,14 +351,26 @@ int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 {
   switch (cls)
   {
-  case 1: return launch_reg<1>(ctx, a);
-  case 2: return launch_reg<2>(ctx, a);
-  case 3: return launch_reg<3>(ctx, a);
-  case 4: return launch_reg<4>(ctx, a);
-  case 5: return launch_reg<5>(ctx, a);
-  case 6: return launch_reg<6>(ctx, a);
-  case 7: return launch_reg<7>(ctx, a);
-  case 8: return launch_reg<8>(ctx, a);
+  case 1: return launch_reg<1, 1>(ctx, a);
+  case 2: return launch_reg<2, 1>(ctx, a);
+  case 3: return launch_reg<3, 1>(ctx, a);
+  case 4: return launch_reg<4, 1>(ctx, a);
+  case 5: return launch_reg<5, 1>(ctx, a);
+  case 6: return launch_reg<6, 1>(ctx, a);
+  case 7: return launch_reg<7, 1>(ctx, a);
+  case 8: return launch_reg<8, 1>(ctx, a);
+  case 9: return launch_reg<5, 2>(ctx, a);
+  case 10: return launch_reg<6, 2>(ctx, a);
+  case 11: return launch_reg<7, 2>(ctx, a);
+  case 12: return launch_reg<8, 2>(ctx, a);
+  case 13: return launch_reg<5, 4>(ctx, a);
+  case 14: return launch_reg<6, 4>(ctx, a);
+  case 15: return launch_reg<7, 4>(ctx, a);
+  case 16: return launch_reg<8, 4>(ctx, a);
+  case 17: return launch_reg<5, 8>(ctx, a);
+  case 18: return launch_reg<6, 8>(ctx, a);
+  case 19: return launch_reg<7, 8>(ctx, a);
+  case 20: return launch_reg<8, 8>(ctx, a);
   default: return fail(ctx, DCPGPU_EINVAL, "bad kernel class");
   }
 }
@@ -354,7 +389,7 @@ int launch_generic(dcpgpu_ctx *ctx, GenArgs a, int max_K)
   a.scratch_stride = stride;
   generic_kernel<TRACE><<<grid, GEN_THREADS, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
-  ctx->last_launches += 1;
+  ctx->launches += 1;
   return 0;
 }
 
@@ -373,8 +408,7 @@ int begin_pass(dcpgpu_ctx *ctx, size_t npairs)
   int rc = sync_profiles(ctx);
   if (rc) return rc;
   if ((rc = ensure(ctx, ctx->d_out, ctx->out_cap, npairs))) return rc;
-  CU(cudaMemsetAsync(ctx->d_counters, 0, 32 * sizeof(unsigned long long), ctx->stream));
-  ctx->last_launches = 0;
+  CU(cudaMemsetAsync(ctx->d_counters, 0, 26 * sizeof(unsigned long long), ctx->stream));
   ctx->last_cells = 0;
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
   return 0;
@@ -389,6 +423,45 @@ int end_pass(dcpgpu_ctx *ctx, int64_t npairs)
 }
 
 } // namespace
+
+template <int MODE>
+static int run_alu_peak(dcpgpu_ctx *ctx, double *tops)
+{
+  int const iters = 4096, threads = 256;
+  int const blocks = ctx->sm_count * 8;
+  float *d = nullptr;
+  CU(cudaMalloc(reinterpret_cast<void **>(&d), (size_t)blocks * threads * sizeof(float)));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep)
+  {
+    cudaEventRecord(a, ctx->stream);
+    alu_peak_kernel<MODE><<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0f + rep);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    if (rep && ms < best) best = ms;
+    ctx->launches += 1;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaError_t e = cudaGetLastError();
+  cudaFree(d);
+  if (e != cudaSuccess) return fail_cuda(ctx, e, "alu_peak");
+  // fp32 lane-operations per iteration and thread.  A three-input min counts as two
+  // operations (it replaces two two-input mins of the recurrence), an f32x2 add as two.
+  double per_iter = 16.0;                 // modes 0, 1, 2: 16 instructions, 16 ops
+  if (MODE == 3) per_iter = 32.0;         // 16 FMNMX3
+  if (MODE == 4) per_iter = 32.0;         // 16 FADD2
+  if (MODE == 5) per_iter = 32.0;         // 16 FADD + 8 FMNMX3
+  double const ops = per_iter * iters * (double)blocks * threads;
+  *tops = ops / (best * 1e-3) / 1e12;
+  return 0;
+}
+
 
 // ---- C ABI -------------------------------------------------------------------------------
 
@@ -607,17 +680,23 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   NodeRef const *drefs = reinterpret_cast<NodeRef const *>(ctx->d_stage + o_refs);
   int const VL = 32 * d.W;
   dim3 const grid((d.Kpad + 127) / 128, NCODES);
-  pack_em_kernel<<<grid, 128, 0, ctx->stream>>>(drefs, K, d.Q, VL, d.Kpad, static_cast<float *>(pem));
+  int *d_bad = reinterpret_cast<int *>(ctx->d_counters + 28);
+  CU(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  pack_em_kernel<<<grid, 128, 0, ctx->stream>>>(drefs, K, d.Q, VL, d.Kpad, static_cast<float *>(pem), d_bad);
   pack_core_kernel<<<(d.Kpad + 127) / 128, 128, 0, ctx->stream>>>(
-      drefs, reinterpret_cast<float const *>(ctx->d_stage + o_bm), K, d.Q, VL, d.Kpad, static_cast<float *>(pcore));
+      drefs, reinterpret_cast<float const *>(ctx->d_stage + o_bm), K, d.Q, VL, d.Kpad, static_cast<float *>(pcore), d_bad);
   pack_nulbg_kernel<<<(NCODES + 127) / 128, 128, 0, ctx->stream>>>(
       reinterpret_cast<float const *>(ctx->d_stage + o_nul), reinterpret_cast<float const *>(ctx->d_stage + o_bg),
-      static_cast<float2 *>(pnb));
+      static_cast<float2 *>(pnb), d_bad);
   CU(cudaGetLastError());
+  int h_bad = 0;
+  CU(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx->launches += 3;
   // the staging buffer is reused by the next call: finish the pack first
   CU(cudaStreamSynchronize(ctx->stream));
 
   ctx->h_profiles.push_back(d);
+  ctx->h_unsafe.push_back(h_bad != 0);
   ctx->profiles_dirty = true;
   if (profile_index) *profile_index = (int32_t)ctx->h_profiles.size() - 1;
   return 0;
@@ -712,33 +791,33 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if (npairs == 0) return end_pass(ctx, 0);
 
   // bucket by kernel class, keeping the caller's order inside a class
-  std::vector<std::vector<long long>> bucket(MAXQ_REG + 1);
+  std::vector<std::vector<long long>> bucket(NCLASS);
   int maxK_generic = 1;
   double cells = 0;
   for (int64_t i = 0; i < npairs; ++i)
   {
     ProfileDesc const &d = ctx->h_profiles[(size_t)pairs[i].profile];
-    int const c = kernel_class(d);
+    int const c = kernel_class(ctx, pairs[i].profile);
     bucket[(size_t)c].push_back(i);
     if (c == 0) maxK_generic = std::max(maxK_generic, d.K);
     cells += (double)pairs[i].len * d.K;
   }
   std::vector<long long> order;
   order.reserve((size_t)npairs);
-  size_t first[MAXQ_REG + 2];
-  for (int c = 0; c <= MAXQ_REG; ++c)
+  size_t first[NCLASS + 1];
+  for (int c = 0; c < NCLASS; ++c)
   {
     first[c] = order.size();
     order.insert(order.end(), bucket[(size_t)c].begin(), bucket[(size_t)c].end());
   }
-  first[MAXQ_REG + 1] = order.size();
+  first[NCLASS] = order.size();
 
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
 
-  for (int c = 0; c <= MAXQ_REG; ++c)
+  for (int c = 0; c < NCLASS; ++c)
   {
     size_t const n = first[c + 1] - first[c];
     if (!n) continue;
@@ -751,7 +830,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     a.nitems = n;
     a.counter = ctx->d_counters + c;
     a.out = ctx->d_out;
-    a.nhits = ctx->d_counters + 16;
+    a.nhits = ctx->d_counters + 24;
     if (c == 0)
     {
       GenArgs g{};
@@ -779,7 +858,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   if ((rc = begin_pass(ctx, npairs))) return rc;
   if (npairs == 0) return end_pass(ctx, 0);
 
-  std::vector<std::vector<int>> bucket(MAXQ_REG + 1);
+  std::vector<std::vector<int>> bucket(NCLASS);
   int maxK_generic = 1;
   double cells = 0;
   // cells = sum over pairs of min(50K, 100000, len) * K
@@ -790,7 +869,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   for (int p = prof0; p < prof1; ++p)
   {
     ProfileDesc const &d = ctx->h_profiles[(size_t)p];
-    int const c = kernel_class(d);
+    int const c = kernel_class(ctx, p);
     bucket[(size_t)c].push_back(p);
     if (c == 0) maxK_generic = std::max(maxK_generic, d.K);
     int const w = std::min(d.K * 50, DCPGPU_MAX_WINDOW);
@@ -799,20 +878,20 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   }
   std::vector<int> flat;
   flat.reserve((size_t)nprof);
-  size_t first[MAXQ_REG + 2];
-  for (int c = 0; c <= MAXQ_REG; ++c)
+  size_t first[NCLASS + 1];
+  for (int c = 0; c < NCLASS; ++c)
   {
     first[c] = flat.size();
     flat.insert(flat.end(), bucket[(size_t)c].begin(), bucket[(size_t)c].end());
   }
-  first[MAXQ_REG + 1] = flat.size();
+  first[NCLASS] = flat.size();
   if ((rc = ensure(ctx, ctx->d_class_profiles, ctx->class_profiles_cap, flat.size()))) return rc;
   CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
 
   // large classes first: the generic kernel (big K) has the longest tail
-  for (int c = 0; c <= MAXQ_REG; ++c)
+  for (int c = 0; c < NCLASS; ++c)
   {
     size_t const n = first[c + 1] - first[c];
     if (!n) continue;
@@ -827,7 +906,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     a.nitems = (unsigned long long)n * (unsigned long long)nseq;
     a.counter = ctx->d_counters + c;
     a.out = ctx->d_out;
-    a.nhits = ctx->d_counters + 16;
+    a.nhits = ctx->d_counters + 24;
     if (c == 0)
     {
       GenArgs g{};
@@ -866,16 +945,17 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
   if (!ctx || cap < 0 || !nhits) return fail(ctx, DCPGPU_EINVAL, "hits_fetch: bad argument");
   CU(cudaSetDevice(ctx->device));
   unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, ctx->d_counters + 16, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&n, ctx->d_counters + 24, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *nhits = (int64_t)n;
   if (!hit_index || cap == 0 || n == 0) return 0;
   long long *d_idx = nullptr;
   CU(cudaMalloc(reinterpret_cast<void **>(&d_idx), (size_t)n * sizeof(long long)));
-  CU(cudaMemsetAsync(ctx->d_counters + 17, 0, sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + 25, 0, sizeof(unsigned long long), ctx->stream));
   long long const N = ctx->last_n;
-  hits_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, N, ctx->d_counters + 17,
+  hits_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, N, ctx->d_counters + 25,
                                                                        (long long)n, d_idx);
+  ctx->launches += 1;
   std::vector<long long> h((size_t)n);
   cudaError_t e = cudaMemcpyAsync(h.data(), d_idx, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
@@ -888,7 +968,7 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
 }
 
 double dcpgpu_last_cells(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_cells : 0.0; }
-int64_t dcpgpu_last_launches(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_launches : 0; }
+int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx) { return ctx ? ctx->launches : 0; }
 
 float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx)
 {
@@ -945,7 +1025,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters + 18, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + 26, 0, 2 * sizeof(unsigned long long), ctx->stream));
 
   GenArgs g{};
   g.s.profiles = ctx->d_profiles;
@@ -954,9 +1034,9 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   g.s.pairs = ctx->d_tpairs;
   g.s.order = nullptr;
   g.s.nitems = n;
-  g.s.counter = ctx->d_counters + 18;
+  g.s.counter = ctx->d_counters + 26;
   g.s.out = ctx->d_tout;
-  g.s.nhits = ctx->d_counters + 19;
+  g.s.nhits = ctx->d_counters + 27;
   g.xnodes = ctx->d_xnodes;
   g.nodes = ctx->d_nodes;
   g.xnode_off = ctx->d_xnode_off;
@@ -1015,6 +1095,7 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
     w.sizes = d_sz;
     walk_write_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(w);
     e = cudaGetLastError();
+    ctx->launches += 1;
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream);
@@ -1043,6 +1124,22 @@ int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t 
     CU(cudaMemcpyAsync(nodes, ctx->d_nodes + ctx->t_node_off[(size_t)i], nn * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s)
+{
+  if (!ctx || !tera_ops_per_s) return DCPGPU_EINVAL;
+  CU(cudaSetDevice(ctx->device));
+  switch (mode)
+  {
+  case 0: return run_alu_peak<0>(ctx, tera_ops_per_s);
+  case 1: return run_alu_peak<1>(ctx, tera_ops_per_s);
+  case 2: return run_alu_peak<2>(ctx, tera_ops_per_s);
+  case 3: return run_alu_peak<3>(ctx, tera_ops_per_s);
+  case 4: return run_alu_peak<4>(ctx, tera_ops_per_s);
+  case 5: return run_alu_peak<5>(ctx, tera_ops_per_s);
+  default: return fail(ctx, DCPGPU_EINVAL, "alu_peak: bad mode");
+  }
 }
 
 int dcpgpu_xtrans(int window_len, uint32_t flags, float out[13])

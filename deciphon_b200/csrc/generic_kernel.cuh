@@ -382,3 +382,58 @@ __global__ void walk_write_kernel(WalkArgs a)
 }
 
 } // namespace dcp
+
+// ---- FP32 ALU issue-rate microbenchmark (the roofline denominator of the score kernel) ----
+// Every operation is pinned with asm volatile so that ptxas cannot fuse or drop any of them.
+// MODE 0: FADD + FMNMX 1:1 (the recurrence's own mix: 17 add : 16 two-input min per cell)
+// MODE 1: FADD only   MODE 2: FMNMX only   MODE 3: FMNMX3 only   MODE 4: FADD2 (f32x2) only
+// MODE 5: FADD + FMNMX3 2:1 (a cell written with three-input mins: 18 add : 9 min3)
+namespace dcp {
+#define DCP_FADD(d, a, b) asm volatile("add.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b))
+#define DCP_FMIN(d, a, b) asm volatile("min.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b))
+#define DCP_FMIN3(d, a, b, c) asm volatile("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c))
+template <int MODE>
+__global__ void __launch_bounds__(256) alu_peak_kernel(float *out, int iters, float seed)
+{
+  float a[8], b[8], c[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+  {
+    a[j] = seed + (float)(threadIdx.x + j);
+    b[j] = seed * 0.5f + (float)j;
+    c[j] = seed * 0.25f + (float)(j * 3);
+  }
+  for (int i = 0; i < iters; ++i)
+  {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+    {
+      if (MODE == 0) { DCP_FADD(a[j], a[j], b[j]); DCP_FMIN(c[j], c[j], a[j]); }
+      if (MODE == 1) { DCP_FADD(a[j], a[j], b[j]); DCP_FADD(c[j], c[j], b[j]); }
+      if (MODE == 2) { DCP_FMIN(a[j], a[j], b[j]); DCP_FMIN(c[j], c[j], b[j]); }
+      if (MODE == 3) { DCP_FMIN3(a[j], a[j], b[j], c[j]); DCP_FMIN3(b[j], b[j], c[j], a[j]); }
+      if (MODE == 5) { DCP_FADD(a[j], a[j], b[j]); DCP_FADD(b[j], b[j], c[j]); DCP_FMIN3(c[j], c[j], a[j], b[j]); }
+    }
+    if (MODE == 4)
+    {
+#pragma unroll
+      for (int j = 0; j < 8; j += 2)
+      {
+        unsigned long long x, y;
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(a[j]), "f"(a[j + 1]));
+        asm volatile("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b[j]), "f"(b[j + 1]));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+        asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+        asm volatile("mov.b64 {%0, %1}, %2;" : "=f"(a[j]), "=f"(a[j + 1]) : "l"(x));
+      }
+    }
+  }
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    s += a[j] + b[j] + c[j];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+} // namespace dcp

@@ -11,9 +11,10 @@
 // which is value-exact (bit-identical) with the reference because fp32 rounding is
 // monotone: min_i((s_i + tau_i) + e) == (min_i (s_i + tau_i)) + e.
 //
-// Mapping: ONE WARP PER PAIR.  The K nodes are striped across the 32 lanes like the
-// reference stripes them across SIMD lanes (viterbi.c:220-221): lane = k / Q, q = k % Q,
-// Q = ceil(K/32) <= 8.  Per lane everything lives in registers:
+// Mapping: W WARPS PER PAIR (W = 1 for K <= 256, 2/4/8 up to K = 2048).  The K nodes are
+// striped across the VL = 32*W "virtual lanes" like the reference stripes them across SIMD
+// lanes (viterbi.c:220-221): vl = k / Q, q = k % Q, Q <= 8.  Per lane everything lives in
+// registers:
 //   * the 8 transition costs of its Q nodes,
 //   * a 5-row ring of P and Q (the reference's 6-slot time frame, viterbi.c:12,160-161;
 //     the row being computed needs no slot of its own here), rotated by unrolling the row
@@ -22,16 +23,22 @@
 // shift(), intrinsics.h:95-106).  The serial delete chain is resolved like the reference's
 // lazy sweeps (viterbi.c:561-580): one in-lane sweep, then boundary propagation repeated
 // while any lane still improves (warp vote) -- every candidate is a left-to-right chain
-// sum, so the fixed point is bit-identical to the serial recurrence.
+// sum, so the fixed point is bit-identical to the serial recurrence.  With W > 1 the warp
+// boundary values (M, I, D of a warp's last node and its partial E) cross through a
+// double-buffered shared-memory mailbox, two CTA barriers per row.
 // The special states are spread over lanes 0..3 (N, J, C and the null model's R), which
 // all run the same "min_t prev[t] + null[code_t]" recurrence.
+//
+// Instruction selection (measured on B200): FADD issues at 1/clk/SMSP on the
+// fma pipe, FMNMX and the three-input FMNMX3 at 1/2 clk on the alu pipe, so every pair of
+// mins is written as one min3 (min.f32 d,a,b,c) and E is reduced with one REDUX.MIN on the
+// bit patterns (all costs are >= +0, checked when a profile is uploaded).
 #pragma once
 #include "layout.cuh"
 #include <math_constants.h>
 
 namespace dcp {
 
-constexpr int SCORE_THREADS = 128;
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 struct ScoreArgs
@@ -53,14 +60,27 @@ struct ScoreArgs
   unsigned long long *nhits;
 };
 
-template <int Q>
-__device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restrict__ row, int lane)
+struct __align__(16) Mail
+{
+  float M, I, D, E;
+};
+
+__device__ __forceinline__ float min3(float a, float b, float c)
+{
+  float d;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
+
+// Row of one code inside the emission table: Q values of virtual lane vl (see layout.cuh).
+template <int Q, int VL>
+__device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restrict__ row, int vl)
 {
   constexpr int N4 = Q / 4;
 #pragma unroll
   for (int c = 0; c < N4; ++c)
   {
-    float4 v = __ldg(reinterpret_cast<float4 const *>(row + c * 128) + lane);
+    float4 v = __ldg(reinterpret_cast<float4 const *>(row + c * 4 * VL) + vl);
     e[4 * c + 0] = v.x;
     e[4 * c + 1] = v.y;
     e[4 * c + 2] = v.z;
@@ -68,25 +88,18 @@ __device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restri
   }
   if constexpr ((Q & 2) != 0)
   {
-    float2 v = __ldg(reinterpret_cast<float2 const *>(row + 32 * (N4 * 4)) + lane);
+    float2 v = __ldg(reinterpret_cast<float2 const *>(row + VL * (N4 * 4)) + vl);
     e[N4 * 4 + 0] = v.x;
     e[N4 * 4 + 1] = v.y;
   }
-  if constexpr ((Q & 1) != 0) e[Q - 1] = __ldg(row + 32 * (Q - 1) + lane);
+  if constexpr ((Q & 1) != 0) e[Q - 1] = __ldg(row + VL * (Q - 1) + vl);
 }
 
-__device__ __forceinline__ float shfl_prev(float v, int lane)
+// E partial of a warp: min over its lanes.  Values are >= +0 (or +INF), so the unsigned
+// order of the bit patterns equals the float order and one REDUX.MIN does the reduction.
+__device__ __forceinline__ float warp_min_nonneg(float v)
 {
-  float r = __shfl_up_sync(FULL_MASK, v, 1);
-  return lane == 0 ? CUDART_INF_F : r; // shift() fills lane 0 with +INF (intrinsics.h:95-106)
-}
-
-__device__ __forceinline__ float warp_min(float v)
-{
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1)
-    v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
-  return v;
+  return __uint_as_float(__reduce_min_sync(FULL_MASK, __float_as_uint(v)));
 }
 
 template <int Q>
@@ -100,113 +113,227 @@ struct Lane
   float xa, xb; // per-lane coefficients of the special-state update
 };
 
-// One DP row l (J = l % 5).  hist = last five nucleotides ending at l-1, 2 bits each.
-template <int Q, int J>
-__device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsigned hist, int lane,
-                                       float NB, float EB, float JB, float &E, float &x)
+template <int Q>
+__device__ __forceinline__ void d_sweep(Lane<Q> const &s, float (&D)[Q])
 {
+#pragma unroll
+  for (int q = 1; q < Q; ++q)
+    D[q] = fminf(D[q], D[q - 1] + s.DD[q]);
+}
+
+// Lazy boundary propagation of the delete chain inside a warp (viterbi.c:569-580).
+// `head`: this lane's predecessor node is not in this warp (its incoming D is handled by
+// the caller).  Returns the final D of node k-1 as seen by q = 0 of every lane.
+template <int Q>
+__device__ __forceinline__ float d_lazy(Lane<Q> const &s, float (&D)[Q], bool head)
+{
+  float din;
+  for (;;)
+  {
+    din = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
+    if (head) din = CUDART_INF_F;
+    float const c = din + s.DD[0];
+    if (!__any_sync(FULL_MASK, c < D[0])) break;
+    D[0] = fminf(D[0], c);
+    d_sweep<Q>(s, D);
+  }
+  return din;
+}
+
+template <int Q>
+__device__ __forceinline__ float e_partial(float const (&M)[Q], float const (&D)[Q])
+{
+  float e = fminf(M[0], D[0]);
+#pragma unroll
+  for (int q = 1; q < Q; ++q)
+    e = min3(e, M[q], D[q]);
+  return warp_min_nonneg(e);
+}
+
+// One DP row l (J = l % 5).  hist = last five nucleotides ending at l-1, 2 bits each.
+template <int Q, int W, int J>
+__device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsigned hist, int lane, int warp,
+                                       float NB, float EB, float JB, Mail *mail, int volatile *flags, int par,
+                                       float &E, float &x)
+{
+  constexpr int VL = 32 * W;
+  int const vl = warp * 32 + lane;
   int code[5];
   code[0] = hist & 3;
   code[1] = 4 + (hist & 15);
   code[2] = 20 + (hist & 63);
   code[3] = 84 + (hist & 255);
   code[4] = 340 + (hist & 1023);
+  constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5, s5 = J;
 
+  // M_k(l), I_k(l) and the special-state recurrences: min over the five emission lengths
   float M[Q], I[Q];
-  float xacc = CUDART_INF_F;
-#pragma unroll
-  for (int t = 1; t <= 5; ++t)
+  float xacc;
   {
-    int const slot = (J - t + 10) % 5;
-    float2 nb = __ldg(pd.nulbg + code[t - 1]);
+    float2 const nb = __ldg(pd.nulbg + code[0]);
     float e[Q];
-    load_chunks<Q>(e, pd.em + (size_t)code[t - 1] * pd.Kpad, lane);
-    if (t == 1)
-    {
+    load_chunks<Q, VL>(e, pd.em + (size_t)code[0] * pd.Kpad, vl);
 #pragma unroll
-      for (int q = 0; q < Q; ++q)
-      {
-        M[q] = s.P[slot][q] + e[q];
-        I[q] = s.Qv[slot][q] + nb.y;
-      }
-      xacc = s.px[slot] + nb.x;
-    }
-    else
+    for (int q = 0; q < Q; ++q)
     {
-#pragma unroll
-      for (int q = 0; q < Q; ++q)
-      {
-        M[q] = fminf(M[q], s.P[slot][q] + e[q]);
-        I[q] = fminf(I[q], s.Qv[slot][q] + nb.y);
-      }
-      xacc = fminf(xacc, s.px[slot] + nb.x);
+      M[q] = s.P[s1][q] + e[q];
+      I[q] = s.Qv[s1][q] + nb.y;
     }
+    xacc = s.px[s1] + nb.x;
+  }
+  {
+    float2 const nb2 = __ldg(pd.nulbg + code[1]);
+    float2 const nb3 = __ldg(pd.nulbg + code[2]);
+    float e2[Q], e3[Q];
+    load_chunks<Q, VL>(e2, pd.em + (size_t)code[1] * pd.Kpad, vl);
+    load_chunks<Q, VL>(e3, pd.em + (size_t)code[2] * pd.Kpad, vl);
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+    {
+      M[q] = min3(M[q], s.P[s2][q] + e2[q], s.P[s3][q] + e3[q]);
+      I[q] = min3(I[q], s.Qv[s2][q] + nb2.y, s.Qv[s3][q] + nb3.y);
+    }
+    xacc = min3(xacc, s.px[s2] + nb2.x, s.px[s3] + nb3.x);
+  }
+  {
+    float2 const nb4 = __ldg(pd.nulbg + code[3]);
+    float2 const nb5 = __ldg(pd.nulbg + code[4]);
+    float e4[Q], e5[Q];
+    load_chunks<Q, VL>(e4, pd.em + (size_t)code[3] * pd.Kpad, vl);
+    load_chunks<Q, VL>(e5, pd.em + (size_t)code[4] * pd.Kpad, vl);
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+    {
+      M[q] = min3(M[q], s.P[s4][q] + e4[q], s.P[s5][q] + e5[q]);
+      I[q] = min3(I[q], s.Qv[s4][q] + nb4.y, s.Qv[s5][q] + nb5.y);
+    }
+    xacc = min3(xacc, s.px[s4] + nb4.x, s.px[s5] + nb5.x);
   }
 
-  // delete chain (viterbi.c:538, 552-580)
+  // Delete chain (viterbi.c:538, 552-580).  Lane 0 of the first warp is node 0, whose
+  // incoming transitions are +INF (protein.c:366-370), so the wrapped shuffle value is inert.
+  bool const head = W > 1 && lane == 0 && warp > 0;
+  float mprev = __shfl_up_sync(FULL_MASK, M[Q - 1], 1);
+  float iprev = __shfl_up_sync(FULL_MASK, I[Q - 1], 1);
+  if (head) mprev = CUDART_INF_F; // arrives through the mailbox below
   float D[Q];
-  float const mprev = shfl_prev(M[Q - 1], lane);
   D[0] = mprev + s.MD[0];
 #pragma unroll
   for (int q = 1; q < Q; ++q)
     D[q] = M[q - 1] + s.MD[q];
-  float din = shfl_prev(D[Q - 1], lane);
-  D[0] = fminf(D[0], din + s.DD[0]);
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    D[q] = fminf(D[q], D[q - 1] + s.DD[q]);
-  for (;;)
   {
-    din = shfl_prev(D[Q - 1], lane);
-    float const c = din + s.DD[0];
-    if (!__any_sync(FULL_MASK, c < D[0])) break;
-    D[0] = fminf(D[0], c);
-#pragma unroll
-    for (int q = 1; q < Q; ++q)
-      D[q] = fminf(D[q], D[q - 1] + s.DD[q]);
+    float din0 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
+    if (head) din0 = CUDART_INF_F;
+    D[0] = fminf(D[0], din0 + s.DD[0]);
+    d_sweep<Q>(s, D);
   }
-  // din now holds the final D of node k-1 for q = 0
+  float dprev = d_lazy<Q>(s, D, head);
 
   // E(l) = min_k min(M_k, D_k)  (viterbi.c:540-558)
-  float e = fminf(M[0], D[0]);
+  float e = e_partial<Q>(M, D);
+  if constexpr (W == 1) { E = e; }
+  else
+  {
+    Mail *box = mail + par * W;
+    if (lane == 31) box[warp] = Mail{M[Q - 1], I[Q - 1], D[Q - 1], e};
+    __syncthreads();
+    if (warp > 0)
+    {
+      Mail const pm = box[warp - 1];
+      float c = CUDART_INF_F;
+      if (lane == 0)
+      {
+        mprev = pm.M;
+        iprev = pm.I;
+        c = fminf(pm.M + s.MD[0], pm.D + s.DD[0]);
+      }
+      if (__any_sync(FULL_MASK, c < D[0]))
+      {
+        float const dlast = D[Q - 1];
+        D[0] = fminf(D[0], c);
+        d_sweep<Q>(s, D);
+        d_lazy<Q>(s, D, head);
+        float const e2 = e_partial<Q>(M, D);
+        if (lane == 31 && (D[Q - 1] != dlast || e2 != e))
+        {
+          box[warp].D = D[Q - 1];
+          box[warp].E = e2;
+          flags[par] = 1;
+        }
+        e = e2;
+      }
+    }
+    for (;;)
+    { // confirm: almost always one barrier; a warp's last D changing after the exchange is rare
+      __syncthreads();
+      if (flags[par] == 0) break;
+      __syncthreads();
+      if (threadIdx.x == 0) flags[par] = 0;
+      __syncthreads();
+      if (warp > 0)
+      {
+        Mail const pm = box[warp - 1];
+        float const c = lane == 0 ? pm.D + s.DD[0] : CUDART_INF_F;
+        if (__any_sync(FULL_MASK, c < D[0]))
+        {
+          float const dlast = D[Q - 1];
+          D[0] = fminf(D[0], c);
+          d_sweep<Q>(s, D);
+          d_lazy<Q>(s, D, head);
+          float const e2 = e_partial<Q>(M, D);
+          if (lane == 31 && (D[Q - 1] != dlast || e2 != e))
+          {
+            box[warp].D = D[Q - 1];
+            box[warp].E = e2;
+            flags[par] = 1;
+          }
+          e = e2;
+        }
+      }
+    }
+    dprev = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
+    if (head) dprev = box[warp - 1].D;
+    float ee = box[0].E;
 #pragma unroll
-  for (int q = 1; q < Q; ++q)
-    e = fminf(e, fminf(M[q], D[q]));
-  E = warp_min(e);
+    for (int w = 1; w < W; ++w)
+      ee = fminf(ee, box[w].E);
+    E = ee;
+  }
 
   // special states: x is N(l) on lane 0, J(l) on lane 1, C(l) on lane 2, R(l) on lane 3
   x = xacc;
   float const N = __shfl_sync(FULL_MASK, x, 0);
   float const Jv = __shfl_sync(FULL_MASK, x, 1);
-  float const B = fminf(fminf(N + NB, E + EB), Jv + JB); // viterbi.c:495-496,582-583
+  float const B = min3(N + NB, E + EB, Jv + JB); // viterbi.c:495-496,582-583
   s.px[J] = fminf(E + s.xa, x + s.xb);
 
-  float const iprev = shfl_prev(I[Q - 1], lane);
   // P(l), Q(l) into the slot that held row l-5
-  s.P[J][0] = fminf(fminf(B + s.BM[0], mprev + s.MM[0]), fminf(iprev + s.IM[0], din + s.DM[0]));
+  s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
 #pragma unroll
   for (int q = 1; q < Q; ++q)
-    s.P[J][q] = fminf(fminf(B + s.BM[q], M[q - 1] + s.MM[q]), fminf(I[q - 1] + s.IM[q], D[q - 1] + s.DM[q]));
+    s.P[J][q] = fminf(min3(B + s.BM[q], M[q - 1] + s.MM[q], I[q - 1] + s.IM[q]), D[q - 1] + s.DM[q]);
 #pragma unroll
   for (int q = 0; q < Q; ++q)
     s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
 }
 
-template <int Q>
-__device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const *__restrict__ words,
-                                          int start, int L, float const *__restrict__ xt, int lane,
-                                          float &null_cost, float &alt_cost)
+template <int Q, int W>
+__device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const *__restrict__ words, int start,
+                                          int L, float const *__restrict__ xt, int lane, int warp, Mail *mail,
+                                          int volatile *flags, float &null_cost, float &alt_cost)
 {
+  constexpr int VL = 32 * W;
   Lane<Q> s;
   int const Kpad = pd.Kpad;
-  load_chunks<Q>(s.BM, pd.core + C_BM * Kpad, lane);
-  load_chunks<Q>(s.MM, pd.core + C_MM * Kpad, lane);
-  load_chunks<Q>(s.MI, pd.core + C_MI * Kpad, lane);
-  load_chunks<Q>(s.MD, pd.core + C_MD * Kpad, lane);
-  load_chunks<Q>(s.IM, pd.core + C_IM * Kpad, lane);
-  load_chunks<Q>(s.II, pd.core + C_II * Kpad, lane);
-  load_chunks<Q>(s.DM, pd.core + C_DM * Kpad, lane);
-  load_chunks<Q>(s.DD, pd.core + C_DD * Kpad, lane);
+  int const vl = warp * 32 + lane;
+  load_chunks<Q, VL>(s.BM, pd.core + C_BM * Kpad, vl);
+  load_chunks<Q, VL>(s.MM, pd.core + C_MM * Kpad, vl);
+  load_chunks<Q, VL>(s.MI, pd.core + C_MI * Kpad, vl);
+  load_chunks<Q, VL>(s.MD, pd.core + C_MD * Kpad, vl);
+  load_chunks<Q, VL>(s.IM, pd.core + C_IM * Kpad, vl);
+  load_chunks<Q, VL>(s.II, pd.core + C_II * Kpad, vl);
+  load_chunks<Q, VL>(s.DM, pd.core + C_DM * Kpad, vl);
+  load_chunks<Q, VL>(s.DD, pd.core + C_DD * Kpad, vl);
 
   float const RR = xt[X_RR], SN = xt[X_SN], NN = xt[X_NN], SB = xt[X_SB], NB = xt[X_NB],
               EB = xt[X_EB], JB = xt[X_JB], EJ = xt[X_EJ], JJ = xt[X_JJ], EC = xt[X_EC],
@@ -249,7 +376,7 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const 
       word = __ldg(++wp);                                                                        \
       left = 16;                                                                                 \
     }                                                                                            \
-    dp_row<Q, JJ_>(s, pd, hist, lane, NB, EB, JB, E, x);                                         \
+    dp_row<Q, W, JJ_>(s, pd, hist, lane, warp, NB, EB, JB, mail, flags, l & 1, E, x);            \
     ++l;                                                                                         \
   }
   int l = 1;
@@ -269,15 +396,41 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const 
   null_cost = R;                    // viterbi.c:718
 }
 
-template <int Q>
-__global__ void __launch_bounds__(SCORE_THREADS) score_reg_kernel(ScoreArgs a)
+template <int W>
+struct ScoreCfg
 {
+  static constexpr int GROUPS = W == 1 ? 4 : 1; // independent pairs per CTA
+  static constexpr int THREADS = 32 * W * GROUPS;
+};
+
+template <int Q, int W>
+__global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreArgs a)
+{
+  __shared__ Mail mail[2 * W];
+  __shared__ int flags[2];
+  __shared__ unsigned long long next_item;
   int const lane = threadIdx.x & 31;
+  int const warp = W == 1 ? 0 : (int)(threadIdx.x >> 5);
+  if (W > 1)
+  {
+    if (threadIdx.x < 2) flags[threadIdx.x] = 0;
+    __syncthreads();
+  }
   for (;;)
   {
     unsigned long long item = 0;
-    if (lane == 0) item = atomicAdd(a.counter, 1ULL);
-    item = __shfl_sync(FULL_MASK, item, 0);
+    if constexpr (W == 1)
+    {
+      if (lane == 0) item = atomicAdd(a.counter, 1ULL);
+      item = __shfl_sync(FULL_MASK, item, 0);
+    }
+    else
+    {
+      if (threadIdx.x == 0) next_item = atomicAdd(a.counter, 1ULL);
+      __syncthreads();
+      item = next_item;
+      __syncthreads();
+    }
     if (item >= a.nitems) break;
 
     int p, sq, start, len;
@@ -308,9 +461,9 @@ __global__ void __launch_bounds__(SCORE_THREADS) score_reg_kernel(ScoreArgs a)
       len = min(w, a.reads.seq_len[sq]);
     }
     float nul, alt;
-    score_one<Q>(pd, a.reads.words + a.reads.seq_word[sq], start, len, a.xt + (size_t)len * X_STRIDE,
-                 lane, nul, alt);
-    if (lane == 0)
+    score_one<Q, W>(pd, a.reads.words + a.reads.seq_word[sq], start, len, a.xt + (size_t)len * X_STRIDE, lane,
+                    warp, mail, flags, nul, alt);
+    if (lane == 0 && warp == 0)
     {
       a.out[oidx] = make_float2(nul, alt);
       float const d = alt - nul; // lrt = -2*((-nul) - (-alt)) >= 0  <=>  alt - nul <= 0

@@ -167,8 +167,14 @@ class Device:
     def last_kernel_ms(self) -> float:
         return float(lib.dcpgpu_last_kernel_ms(self._h))
 
-    def last_launches(self) -> int:
-        return int(lib.dcpgpu_last_launches(self._h))
+    def launch_count(self) -> int:
+        return int(lib.dcpgpu_launch_count(self._h))
+
+    def alu_peak(self, mode: int = 0) -> float:
+        """Measured FP32 non-tensor issue rate, tera lane-ops/s (see include/dcpgpu.h)."""
+        v = C.c_double()
+        self._check(lib.dcpgpu_alu_peak(self._h, mode, C.byref(v)))
+        return v.value
 
     # -- trace pass ----------------------------------------------------------------------
     def trace_pairs(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):

@@ -96,21 +96,24 @@ def random_read(rng: np.random.Generator, L: int) -> np.ndarray:
 
 def mutate(rng: np.random.Generator, x: np.ndarray, rate: float) -> np.ndarray:
     """Error channel: each base is hit with probability `rate`; 1/3 sub, 1/3 ins, 1/3 del."""
-    out = []
-    u = rng.random(len(x))
-    kind = rng.integers(0, 3, size=len(x))
-    rnd = rng.integers(0, 4, size=len(x), dtype=np.uint8)
-    for i in range(len(x)):
-        if u[i] >= rate:
-            out.append(x[i])
-        elif kind[i] == 0:
-            out.append((x[i] + 1 + rnd[i] % 3) % 4)
-        elif kind[i] == 1:
-            out.append(rnd[i])
-            out.append(x[i])
-    if not out:
-        out = [x[0] if len(x) else 0]
-    return np.asarray(out, dtype=np.uint8)
+    n = len(x)
+    if n == 0:
+        return np.zeros(1, dtype=np.uint8)
+    hit = rng.random(n) < rate
+    kind = rng.integers(0, 3, size=n)
+    rnd = rng.integers(0, 4, size=n, dtype=np.uint8)
+    sub = hit & (kind == 0)
+    ins = hit & (kind == 1)
+    dele = hit & (kind == 2)
+    base = np.where(sub, (x + 1 + rnd % 3) % 4, x).astype(np.uint8)
+    counts = np.where(dele, 0, np.where(ins, 2, 1))
+    out = np.repeat(base, counts)
+    # the first copy of an inserted position becomes the random base
+    first = np.cumsum(counts) - counts
+    out[first[ins]] = rnd[ins]
+    if out.size == 0:
+        out = x[:1].copy()
+    return np.ascontiguousarray(out, dtype=np.uint8)
 
 
 def consensus_dna(pool: NodePool, node_ids: np.ndarray) -> np.ndarray:

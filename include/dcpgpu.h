@@ -117,7 +117,8 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
 /* DP cells (sum of len*K) of the last score pass, and device ms of its kernels. */
 double dcpgpu_last_cells(dcpgpu_ctx const *ctx);
 float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx);
-int64_t dcpgpu_last_launches(dcpgpu_ctx const *ctx);
+/* Cumulative number of kernels this library has launched on the context. */
+int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx);
 
 /* ---- trace pass: viterbi_path + trellis_unzip for the given (hit) pairs -----------------
  * Builds the reference's bit-packed trellis (trellis.h:12-56) on the device, walks it
@@ -130,6 +131,11 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
                        uint8_t *seqsizes);
 /* Raw trellis words of traced pair i: xnodes[len+1], nodes[(len+1)*K] (tests, debugging). */
 int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t *nodes);
+
+/* Measured non-tensor FP32 issue rate of this GPU in tera lane-operations per second (the
+ * roofline denominator of the score kernel).  mode 0: FADD+FMNMX 1:1 (the DP's mix),
+ * 1: FADD, 2: FMNMX, 3: FMNMX3 (one op each), 4: FADD2, 5: FADD2+FMNMX3. */
+int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s);
 
 /* The 13 special-transition costs for a window of window_len nucleotides, in the order
  * RR,SN,NN,SB,NB,EB,JB,EJ,JJ,EC,CC,ET,CT (viterbi.h:4-19), as the device uses them. */

@@ -92,7 +92,8 @@ def test_trace_matches_reference_paths(device, golden_dev, ref_vectors):
     assert at == len(key)
 
 
-@pytest.mark.parametrize("K", [1, 2, 3, 5, 31, 32, 33, 64, 97, 128, 160, 161, 200, 224, 225, 255, 256, 257, 300, 520, 1100])
+@pytest.mark.parametrize("K", [1, 2, 3, 5, 31, 32, 33, 64, 97, 128, 160, 161, 200, 224, 225, 255, 256,
+                               257, 300, 384, 400, 512, 513, 700, 1000, 1024, 1100, 1500, 2000, 2048, 2100])
 def test_score_and_trace_synthetic_K(device, oracle, node_pool, K):
     """Every kernel class (Q = 1..8 register kernels and the generic kernel) against the oracle:
     scores bit-exact, trellis words bit-exact, paths identical; unaligned window starts."""
@@ -173,9 +174,28 @@ def test_against_compiled_reference(device, reference, oracle, node_pool):
                 assert np.array_equal(paths[i][0], rids) and np.array_equal(paths[i][1], rsz)
 
 
+def test_unsafe_profile_takes_generic_kernel(device, oracle, node_pool):
+    """A profile with a positive log-prob (negative cost) must not run on the register kernels,
+    whose E reduction orders bit patterns as unsigned; results still match the oracle."""
+    rng = np.random.default_rng(5)
+    prof = synth.synth_profile(rng, 64, node_pool)
+    prof.trans = prof.trans.copy()
+    prof.trans[10, 0] = 0.25  # MM log-prob > 0
+    costs = prof.costs()
+    p = device.add_profile(prof)
+    reads = [synth.random_read(rng, 300), synth.random_read(rng, 77)]
+    device.set_reads(reads)
+    nul, alt = device.score_pairs(_pairs([(p, i, 0, len(x)) for i, x in enumerate(reads)]), True, False)
+    for i, x in enumerate(reads):
+        xt = oracle.xtrans(len(x), True, False)
+        assert _bits(nul[i:i + 1])[0] == _bits(oracle.null(costs[0], xt, x).reshape(1))[0]
+        assert _bits(alt[i:i + 1])[0] == _bits(oracle.alt(costs, xt, x).reshape(1))[0]
+
+
 def test_empty_and_invalid(device, golden_dev):
     base, reads = golden_dev
     from deciphon_b200.device import DcpGpuError
+    device.set_reads(reads)
     nul, alt = device.score_pairs(_pairs([]))
     assert len(nul) == 0 and len(alt) == 0
     with pytest.raises(DcpGpuError):
