@@ -62,15 +62,7 @@ def profile_nodes(seed: int, p: int, K: int, pool):
     return synth.synth_profile_nodes(rng, int(K), pool)
 
 
-def shard_bounds(sizes: np.ndarray, world: int):
-    """Contiguous profile ranges balanced by sum of core sizes."""
-    csum = np.concatenate([[0], np.cumsum(sizes)])
-    total = csum[-1]
-    cuts = [0]
-    for r in range(1, world):
-        cuts.append(int(np.searchsorted(csum, total * r / world)))
-    cuts.append(len(sizes))
-    return cuts
+from deciphon_b200.shard import shard_bounds  # noqa: E402
 
 
 def make_reads(seed: int, first: int, count: int, L: int, sizes: np.ndarray, pool, err=0.10, frac=0.01):

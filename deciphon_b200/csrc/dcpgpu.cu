@@ -336,12 +336,19 @@ template <int Q, int W>
 int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
 {
   constexpr int T = ScoreCfg<W>::THREADS, G = ScoreCfg<W>::GROUPS;
+  constexpr size_t SMEM = score_smem_bytes<Q, W>();
+  static bool configured = false;
+  if (!configured)
+  {
+    CU(cudaFuncSetAttribute(score_reg_kernel<Q, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    configured = true;
+  }
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W>, T, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W>, T, SMEM));
   if (per_sm < 1) per_sm = 1;
   unsigned long long const want = (a.nitems + G - 1) / G;
   unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  score_reg_kernel<Q, W><<<grid, T, 0, ctx->stream>>>(a);
+  score_reg_kernel<Q, W><<<grid, T, SMEM, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return 0;

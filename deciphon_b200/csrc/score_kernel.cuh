@@ -29,10 +29,18 @@
 // The special states are spread over lanes 0..3 (N, J, C and the null model's R), which
 // all run the same "min_t prev[t] + null[code_t]" recurrence.
 //
-// Instruction selection (measured on B200): FADD issues at 1/clk/SMSP on the
-// fma pipe, FMNMX and the three-input FMNMX3 at 1/2 clk on the alu pipe, so every pair of
-// mins is written as one min3 (min.f32 d,a,b,c) and E is reduced with one REDUX.MIN on the
-// bit patterns (all costs are >= +0, checked when a profile is uploaded).
+// Emission tables: the rows of the three short code classes (1-, 2-, 3-mers: 84 rows, L1
+// resident) are read with coalesced 128-bit loads.  With W > 1 the rows of the 4- and 5-mers
+// (1280 rows, L2/HBM resident) are staged into shared memory by TMA (cp.async.bulk + mbarrier
+// complete_tx), five DP rows ahead, through a 5-stage ring whose stage index is the row's
+// compile-time ring slot -- so the L2 latency never sits on the row's critical path.  With
+// W = 1 (1 KB rows per warp) the same ring measured slower than plain loads and is off.
+//
+// Instruction selection (measured on B200 with dcpgpu_alu_peak): FADD and the
+// two-input FMNMX both issue at ~1 warp-instruction/clk/SMSP, the three-input FMNMX3 at 1/2
+// but it replaces two mins and frees an issue slot for the other pipe, so every pair of mins
+// is written as one min3 (min.f32 d,a,b,c); E is reduced with one CREDUX.MIN on the bit
+// patterns (all costs are >= +0, checked when a profile is uploaded).
 #pragma once
 #include "layout.cuh"
 #include <math_constants.h>
@@ -72,6 +80,42 @@ __device__ __forceinline__ float min3(float a, float b, float c)
   return d;
 }
 
+namespace tma {
+__device__ __forceinline__ uint32_t smem_u32(void const *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, void const *src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+  asm volatile("{\n\t"
+               ".reg .pred P1;\n\t"
+               "LAB_WAIT:\n\t"
+               "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+               "@P1 bra DONE;\n\t"
+               "bra LAB_WAIT;\n\t"
+               "DONE:\n\t"
+               "}" ::"r"(bar),
+               "r"(parity)
+               : "memory");
+}
+} // namespace tma
+
 // Row of one code inside the emission table: Q values of virtual lane vl (see layout.cuh).
 template <int Q, int VL>
 __device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restrict__ row, int vl)
@@ -95,12 +139,65 @@ __device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restri
   if constexpr ((Q & 1) != 0) e[Q - 1] = __ldg(row + VL * (Q - 1) + vl);
 }
 
+// Same row layout, read from a TMA-filled shared-memory stage (conflict-free LDS.128/64/32).
+template <int Q, int VL>
+__device__ __forceinline__ void load_chunks_smem(float (&e)[Q], float const *row, int vl)
+{
+  constexpr int N4 = Q / 4;
+#pragma unroll
+  for (int c = 0; c < N4; ++c)
+  {
+    float4 v = *(reinterpret_cast<float4 const *>(row + c * 4 * VL) + vl);
+    e[4 * c + 0] = v.x;
+    e[4 * c + 1] = v.y;
+    e[4 * c + 2] = v.z;
+    e[4 * c + 3] = v.w;
+  }
+  if constexpr ((Q & 2) != 0)
+  {
+    float2 v = *(reinterpret_cast<float2 const *>(row + VL * (N4 * 4)) + vl);
+    e[N4 * 4 + 0] = v.x;
+    e[N4 * 4 + 1] = v.y;
+  }
+  if constexpr ((Q & 1) != 0) e[Q - 1] = row[VL * (Q - 1) + vl];
+}
+
+// The TMA ring of one pair: 5 stages (ring slot J) x 2 rows (4-mer, 5-mer) x ROW floats.
+template <int Q, int W>
+struct Ring
+{
+  static constexpr int ROW = 32 * W * Q;          // floats per code row
+  static constexpr uint32_t ROW_BYTES = ROW * 4u; // multiple of 128
+  float *stage;                                   // [5][2][ROW]
+  uint32_t stage_addr;                            // shared-space address of stage
+  uint32_t bar_addr;                              // shared-space address of full[5]
+  // issue the copies of the row whose last five nucleotides are `h` into ring slot j
+  __device__ __forceinline__ void fill(ProfileDesc const &pd, int j, unsigned h) const
+  {
+    uint32_t const bar = bar_addr + 8u * (uint32_t)j;
+    uint32_t const dst = stage_addr + (uint32_t)j * 2u * ROW_BYTES;
+    tma::mbar_arrive_expect_tx(bar, 2u * ROW_BYTES);
+    tma::bulk_g2s(dst, pd.em + (size_t)(84 + (h & 255u)) * ROW, ROW_BYTES, bar);
+    tma::bulk_g2s(dst + ROW_BYTES, pd.em + (size_t)(340 + (h & 1023u)) * ROW, ROW_BYTES, bar);
+  }
+};
+
 // E partial of a warp: min over its lanes.  Values are >= +0 (or +INF), so the unsigned
 // order of the bit patterns equals the float order and one REDUX.MIN does the reduction.
 __device__ __forceinline__ float warp_min_nonneg(float v)
 {
   return __uint_as_float(__reduce_min_sync(FULL_MASK, __float_as_uint(v)));
 }
+
+template <int W>
+struct ScoreCfg
+{
+  static constexpr int GROUPS = W == 1 ? 4 : 1; // independent pairs per CTA
+  static constexpr int THREADS = 32 * W * GROUPS;
+  // Long-code rows through the TMA ring?  Measured on B200 (profiles/): CTA-wide bulk copies
+  // (W > 1, 2..8 KB each) beat per-lane loads, 1 KB per-warp copies (W = 1) do not.
+  static constexpr bool TMA_RING = W > 1;
+};
 
 template <int Q>
 struct Lane
@@ -152,7 +249,8 @@ __device__ __forceinline__ float e_partial(float const (&M)[Q], float const (&D)
 
 // One DP row l (J = l % 5).  hist = last five nucleotides ending at l-1, 2 bits each.
 template <int Q, int W, int J>
-__device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsigned hist, int lane, int warp,
+__device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q, W> const &ring, unsigned hist,
+                                       unsigned hist_ahead, bool refill, unsigned &phase, int lane, int warp,
                                        float NB, float EB, float JB, Mail *mail, int volatile *flags, int par,
                                        float &E, float &x)
 {
@@ -199,8 +297,18 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsign
     float2 const nb4 = __ldg(pd.nulbg + code[3]);
     float2 const nb5 = __ldg(pd.nulbg + code[4]);
     float e4[Q], e5[Q];
-    load_chunks<Q, VL>(e4, pd.em + (size_t)code[3] * pd.Kpad, vl);
-    load_chunks<Q, VL>(e5, pd.em + (size_t)code[4] * pd.Kpad, vl);
+    if constexpr (ScoreCfg<W>::TMA_RING)
+    { // the 4- and 5-mer rows of this DP row were requested five rows ago
+      tma::mbar_wait(ring.bar_addr + 8u * J, (phase >> J) & 1u);
+      phase ^= 1u << J;
+      load_chunks_smem<Q, VL>(e4, ring.stage + (J * 2 + 0) * Ring<Q, W>::ROW, vl);
+      load_chunks_smem<Q, VL>(e5, ring.stage + (J * 2 + 1) * Ring<Q, W>::ROW, vl);
+    }
+    else
+    {
+      load_chunks<Q, VL>(e4, pd.em + (size_t)code[3] * pd.Kpad, vl);
+      load_chunks<Q, VL>(e5, pd.em + (size_t)code[4] * pd.Kpad, vl);
+    }
 #pragma unroll
     for (int q = 0; q < Q; ++q)
     {
@@ -208,6 +316,10 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsign
       I[q] = min3(I[q], s.Qv[s4][q] + nb4.y, s.Qv[s5][q] + nb5.y);
     }
     xacc = min3(xacc, s.px[s4] + nb4.x, s.px[s5] + nb5.x);
+  }
+  if constexpr (W == 1 && ScoreCfg<W>::TMA_RING)
+  { // slot J is consumed: request row l+5 into it (one elected lane drives the TMA)
+    if (refill && lane == 0) ring.fill(pd, J, hist_ahead);
   }
 
   // Delete chain (viterbi.c:538, 552-580).  Lane 0 of the first warp is node 0, whose
@@ -237,6 +349,8 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsign
     Mail *box = mail + par * W;
     if (lane == 31) box[warp] = Mail{M[Q - 1], I[Q - 1], D[Q - 1], e};
     __syncthreads();
+    // every warp has consumed ring slot J: request row l+5 into it
+    if (ScoreCfg<W>::TMA_RING && refill && threadIdx.x == 0) ring.fill(pd, J, hist_ahead);
     if (warp > 0)
     {
       Mail const pm = box[warp - 1];
@@ -318,8 +432,9 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, unsign
 }
 
 template <int Q, int W>
-__device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const *__restrict__ words, int start,
-                                          int L, float const *__restrict__ xt, int lane, int warp, Mail *mail,
+__device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> const &ring, unsigned &phase,
+                                          uint32_t const *__restrict__ words, int start, int L,
+                                          float const *__restrict__ xt, int lane, int warp, Mail *mail,
                                           int volatile *flags, float &null_cost, float &alt_cost)
 {
   constexpr int VL = 32 * W;
@@ -358,25 +473,42 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const 
   s.xb = lane == 0 ? NN : lane == 1 ? JJ : lane == 2 ? CC : lane == 3 ? RR : CUDART_INF_F;
   s.px[0] = lane == 0 ? (0.0f + SN) : lane == 3 ? ((-RR) + RR) : CUDART_INF_F;
 
-  // nucleotide stream
+  // Nucleotide stream, running five positions ahead of the DP row: H holds the last ten
+  // nucleotides, bits 10..19 = the five ending at l-1 (this row's codes), bits 0..9 = the five
+  // ending at l+4 (the codes of row l+5, whose long-code rows are requested now).
   int g = start;
   uint32_t const *wp = words + (g >> 4);
   uint32_t word = __ldg(wp) >> (2 * (g & 15));
   int left = 16 - (g & 15);
-  unsigned hist = 0;
-  float E = CUDART_INF_F, x = CUDART_INF_F;
-
-#define DCP_ROW(JJ_)                                                                             \
+  unsigned H = 0;
+#define DCP_NEXT_NT()                                                                            \
   {                                                                                              \
-    if (l > L) break;                                                                            \
-    hist = ((hist << 2) | (word & 3u)) & 1023u;                                                  \
+    H = ((H << 2) | (word & 3u)) & 0xFFFFFu;                                                     \
     word >>= 2;                                                                                  \
     if (--left == 0)                                                                             \
     {                                                                                            \
       word = __ldg(++wp);                                                                        \
       left = 16;                                                                                 \
     }                                                                                            \
-    dp_row<Q, W, JJ_>(s, pd, hist, lane, warp, NB, EB, JB, mail, flags, l & 1, E, x);            \
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i)
+    DCP_NEXT_NT()
+  // prologue: rows 1..5 (slots 1,2,3,4,0); row r ends at nucleotide r-1
+  if (ScoreCfg<W>::TMA_RING && (W == 1 ? lane : (int)threadIdx.x) == 0)
+  {
+#pragma unroll
+    for (int r = 1; r <= 5; ++r)
+      if (r <= L) ring.fill(pd, r % 5, H >> (2 * (5 - r)));
+  }
+  float E = CUDART_INF_F, x = CUDART_INF_F;
+
+#define DCP_ROW(JJ_)                                                                             \
+  {                                                                                              \
+    if (l > L) break;                                                                            \
+    DCP_NEXT_NT()                                                                                \
+    dp_row<Q, W, JJ_>(s, pd, ring, H >> 10, H & 1023u, l + 5 <= L, phase, lane, warp, NB, EB, JB, mail, flags,  \
+                      l & 1, E, x);                                                              \
     ++l;                                                                                         \
   }
   int l = 1;
@@ -389,6 +521,7 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const 
     DCP_ROW(0)
   }
 #undef DCP_ROW
+#undef DCP_NEXT_NT
 
   float const C = __shfl_sync(FULL_MASK, x, 2);
   float const R = __shfl_sync(FULL_MASK, x, 3);
@@ -396,26 +529,45 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, uint32_t const 
   null_cost = R;                    // viterbi.c:718
 }
 
-template <int W>
-struct ScoreCfg
+
+template <int Q, int W>
+constexpr size_t score_smem_bytes()
 {
-  static constexpr int GROUPS = W == 1 ? 4 : 1; // independent pairs per CTA
-  static constexpr int THREADS = 32 * W * GROUPS;
-};
+  return ScoreCfg<W>::TMA_RING ? (size_t)ScoreCfg<W>::GROUPS * (5 * 2 * Ring<Q, W>::ROW * sizeof(float) + 64) : 256;
+}
 
 template <int Q, int W>
 __global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreArgs a)
 {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ Mail mail[2 * W];
   __shared__ int flags[2];
   __shared__ unsigned long long next_item;
   int const lane = threadIdx.x & 31;
-  int const warp = W == 1 ? 0 : (int)(threadIdx.x >> 5);
+  int const group = W == 1 ? (int)(threadIdx.x >> 5) : 0; // independent pair slot inside the CTA
+  int const warp = W == 1 ? 0 : (int)(threadIdx.x >> 5);  // warp index inside the pair
+
+  // carve the TMA ring of this group: stages first (128-byte aligned), then the mbarriers
+  constexpr size_t STAGE_BYTES = 5 * 2 * Ring<Q, W>::ROW * sizeof(float);
+  Ring<Q, W> ring;
+  ring.stage = reinterpret_cast<float *>(dyn_smem + (size_t)group * STAGE_BYTES);
+  ring.stage_addr = tma::smem_u32(ring.stage);
+  ring.bar_addr = tma::smem_u32(dyn_smem + (size_t)ScoreCfg<W>::GROUPS * STAGE_BYTES + (size_t)group * 64);
+  if (ScoreCfg<W>::TMA_RING && (W == 1 ? lane : (int)threadIdx.x) == 0)
+  {
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+      tma::mbar_init(ring.bar_addr + 8u * j, 1);
+    tma::fence_barrier_init();
+  }
+  unsigned phase = 0; // parity of the next completion of each ring slot's mbarrier
   if (W > 1)
   {
     if (threadIdx.x < 2) flags[threadIdx.x] = 0;
     __syncthreads();
   }
+  else
+    __syncwarp();
   for (;;)
   {
     unsigned long long item = 0;
@@ -461,8 +613,8 @@ __global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreAr
       len = min(w, a.reads.seq_len[sq]);
     }
     float nul, alt;
-    score_one<Q, W>(pd, a.reads.words + a.reads.seq_word[sq], start, len, a.xt + (size_t)len * X_STRIDE, lane,
-                    warp, mail, flags, nul, alt);
+    score_one<Q, W>(pd, ring, phase, a.reads.words + a.reads.seq_word[sq], start, len,
+                    a.xt + (size_t)len * X_STRIDE, lane, warp, mail, flags, nul, alt);
     if (lane == 0 && warp == 0)
     {
       a.out[oidx] = make_float2(nul, alt);

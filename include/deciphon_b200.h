@@ -1,0 +1,99 @@
+/*
+ * deciphon_b200.h -- the reference's public scan API, served by the B200 scan path.
+ *
+ * Same names, argument meaning and error behaviour as c-core/deciphon.h:9-32 (mirrored in
+ * python-core/deciphon_core/interface.h:1-40), so that python-core's cffi layer can dlopen
+ * libdeciphon_b200.so instead of libdeciphon.  Behind these entry points the per-window
+ * loop of c-core/thread.c:49-208 runs as waves of batched GPU passes through the C ABI of
+ * include/dcpgpu.h.  What differs from the reference, by design:
+ *
+ *   * dcp_scan_setup: `num_threads` and `cache` are accepted and ignored (the GPU holds every
+ *     profile resident; c-core/scan.c:95-152).  The environment variable DCP_GPU_DEVICE picks
+ *     the CUDA device (default 0).
+ *   * HMMER daemon (c-core/hmmer.c, thread.c:185-203): the third-party client libraries are
+ *     not part of this build.  `port <= 0` runs WITHOUT the HMMER confirmation stage: every
+ *     window with lrt >= 0 and a B..E segment yields a row, `evalue` is written as 0 and no
+ *     .h3r files are produced.  `port > 0` returns DCP_EH3CDIAL.
+ *   * dcp_press_* (c-core/press.c) is outside the hot path: the functions exist and return
+ *     DCP_EFUNCUSE.
+ *   * new error codes are appended after DCP_EINVALNUMPROTEINS = 80.
+ */
+#ifndef DECIPHON_B200_H
+#define DECIPHON_B200_H
+
+#include <stdbool.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+struct dcp_scan;
+struct dcp_batch;
+struct dcp_press;
+
+struct dcp_scan *dcp_scan_new(void);
+void dcp_scan_del(struct dcp_scan const *);
+int dcp_scan_setup(struct dcp_scan *, char const *dbfile, int port, int num_threads, bool multi_hits,
+                   bool hmmer3_compat, bool cache, void (*callback)(void *), void *userdata);
+int dcp_scan_run(struct dcp_scan *, struct dcp_batch *, char const *product_dir);
+void dcp_scan_interrupt(struct dcp_scan *);
+int dcp_scan_progress(struct dcp_scan const *);
+
+struct dcp_press *dcp_press_new(void);
+int dcp_press_setup(struct dcp_press *, int gencode_id, float epsilon);
+int dcp_press_open(struct dcp_press *, char const *hmm, char const *db);
+long dcp_press_nproteins(struct dcp_press const *);
+int dcp_press_next(struct dcp_press *);
+bool dcp_press_end(struct dcp_press const *);
+int dcp_press_close(struct dcp_press *);
+void dcp_press_del(struct dcp_press const *);
+
+struct dcp_batch *dcp_batch_new(void);
+void dcp_batch_del(struct dcp_batch *);
+int dcp_batch_add(struct dcp_batch *, long id, char const *name, char const *data);
+void dcp_batch_reset(struct dcp_batch *);
+
+char const *dcp_error_string(int error_code);
+
+/* Extension: parse a .dcp database (either float encoding) without touching
+ * the GPU; reports the number of profiles, the total core size and epsilon. */
+int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size, float *epsilon);
+
+/* Error codes 1..80 are the reference's (c-core/deciphon.h:34-116); only the ones this
+ * library can return are named here.  81.. are new. */
+enum
+{
+  DCP_EFDATA = 3,
+  DCP_EFREAD = 5,
+  DCP_EFUNCUSE = 8,
+  DCP_EFWRITE = 9,
+  DCP_EZEROSEQ = 11,
+  DCP_EDECODON = 14,
+  DCP_ENOMEM = 20,
+  DCP_EOPENDB = 21,
+  DCP_EWRITEPROD = 39,
+  DCP_ELONGACCESSION = 41,
+  DCP_EMANYTHREADS = 42,
+  DCP_EMKDIR = 45,
+  DCP_EGENCODEID = 50,
+  DCP_EH3CDIAL = 51,
+  DCP_ESEQABC = 57,
+  DCP_ELARGECORESIZE = 63,
+  DCP_EENDOFFILE = 66,
+  DCP_EDBVERSION = 68,
+  DCP_ENOTDBFILE = 69,
+  DCP_ENUCLTNOSUPPORT = 71,
+  DCP_EDBDNASEQRNA = 72,
+  DCP_EDBRNASEQDNA = 73,
+  DCP_ENUCLTSEQTU = 74,
+  DCP_EINVALNUMPROTEINS = 80,
+  DCP_EGPUNODEVICE = 81, /* no CUDA device: this library has no CPU fallback */
+  DCP_EGPUFAIL = 82,     /* a CUDA call failed */
+  DCP_EGPUNOMEM = 83,    /* device memory exhausted */
+  DCP_EGPUINTERNAL = 84, /* invalid argument / state inside the GPU layer */
+};
+
+#ifdef __cplusplus
+}
+#endif
+#endif
