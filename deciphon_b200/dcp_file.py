@@ -280,3 +280,95 @@ def read_dcp(path: str) -> Database:
         protein_sizes=sizes,
         proteins=prots,
     )
+
+
+# ---- writer (current encoding: c-core/write.c:59-66 `bin` + host-endian floats) ---------------
+
+def _mp_str(s: str) -> bytes:
+    b = s.encode()
+    if len(b) < 32:
+        return bytes([0xA0 | len(b)]) + b
+    if len(b) < 256:
+        return bytes([0xD9, len(b)]) + b
+    return bytes([0xDA]) + struct.pack(">H", len(b)) + b
+
+
+def _mp_int(v: int) -> bytes:
+    if 0 <= v < 128:
+        return bytes([v])
+    if 0 <= v < 1 << 16:
+        return bytes([0xCD]) + struct.pack(">H", v)
+    return bytes([0xCE]) + struct.pack(">I", v)
+
+
+def _mp_map(n: int) -> bytes:
+    return bytes([0x80 | n]) if n < 16 else (bytes([0xDE]) + struct.pack(">H", n) if n < 1 << 16 else bytes([0xDF]) + struct.pack(">I", n))
+
+
+def _mp_arr(n: int) -> bytes:
+    return bytes([0x90 | n]) if n < 16 else (bytes([0xDC]) + struct.pack(">H", n) if n < 1 << 16 else bytes([0xDD]) + struct.pack(">I", n))
+
+
+def _mp_f32bin(a) -> bytes:
+    raw = np.ascontiguousarray(a, dtype="<f4").tobytes()
+    n = len(raw)
+    head = bytes([0xC4, n]) if n < 256 else (bytes([0xC5]) + struct.pack(">H", n) if n < 1 << 16 else bytes([0xC6]) + struct.pack(">I", n))
+    return head + raw
+
+
+def _mp_f32ext(a) -> bytes:
+    raw = np.ascontiguousarray(a, dtype=">f4").tobytes()
+    n = len(raw)
+    head = bytes([0xC7, n]) if n < 256 else (bytes([0xC8]) + struct.pack(">H", n) if n < 1 << 16 else bytes([0xC9]) + struct.pack(">I", n))
+    return head + bytes([8]) + raw
+
+
+def write_dcp(path: str, profiles, epsilon: float = 0.01, entry_dist: int = 2, encoding: str = "bin",
+              symbols: str = "ACGT"):
+    """Write profiles as a .dcp file in the reference's key order (database_writer.c:158-193,
+    protein.c:234-281).  `encoding` selects the float-array form: "bin" (current writer) or
+    "ext" (the golden file's older form).  The alphabet sub-maps are written like the golden
+    file's (their current encoding is defined inside third-party imm)."""
+    f32 = _mp_f32bin if encoding == "bin" else _mp_f32ext
+
+    def nuclt(d):
+        a4, a125 = d if d is not None else (np.log(np.full(4, 0.25, np.float32)), np.zeros(125, np.float32))
+        return _mp_arr(2) + f32(a4) + f32(a125)
+
+    def abc(sym, typeid):
+        return (_mp_map(4) + _mp_str("symbols") + _mp_str(sym) + _mp_str("idx") + bytes([0xC7, 94, 0]) + bytes([0x7F] * 94)
+                + _mp_str("any_symbol_id") + _mp_int(55) + _mp_str("typeid") + _mp_int(typeid))
+
+    recs = []
+    for p in profiles:
+        K = p.core_size
+        nd4, nd125 = p.node_nuclt if p.node_nuclt is not None else (None, None)
+        b = _mp_map(10)
+        b += _mp_str("accession") + _mp_str(p.accession)
+        b += _mp_str("gencode") + _mp_int(p.gencode)
+        b += _mp_str("consensus") + _mp_str(p.consensus)
+        b += _mp_str("core_size") + _mp_int(K)
+        b += _mp_str("null_nuclt_dist") + nuclt(p.null_nuclt)
+        b += _mp_str("null_emission") + f32(p.null_emission)
+        b += _mp_str("bg_nuclt_dist") + nuclt(p.bg_nuclt)
+        b += _mp_str("bg_emission") + f32(p.bg_emission)
+        b += _mp_str("nodes") + _mp_map(3 * (K + 1))
+        for i in range(K + 1):
+            b += _mp_str("nuclt_dist") + nuclt(None if nd4 is None else (nd4[i], nd125[i]))
+            b += _mp_str("trans") + f32(p.trans[i])
+            b += _mp_str("emission") + f32(p.emission[i])
+        b += _mp_str("BMk") + f32(p.BMk)
+        recs.append(b)
+    hdr = _mp_map(8)
+    hdr += _mp_str("magic_number") + _mp_int(MAGIC_NUMBER)
+    hdr += _mp_str("version") + _mp_int(1)
+    hdr += _mp_str("entry_dist") + _mp_int(entry_dist)
+    hdr += _mp_str("epsilon") + bytes([0xCA]) + struct.pack(">f", epsilon)
+    hdr += _mp_str("abc") + abc(symbols, 4 if symbols == "ACGT" else 5)
+    hdr += _mp_str("amino") + abc("ACDEFGHIKLMNPQRSTVWY", 2)
+    hdr += _mp_str("has_ga") + bytes([0xC3])
+    hdr += _mp_str("protein_sizes") + _mp_arr(len(recs)) + b"".join(_mp_int(len(r)) for r in recs)
+    with open(path, "wb") as fh:
+        fh.write(_mp_map(2) + _mp_str("header") + hdr + _mp_str("proteins") + _mp_arr(len(recs)))
+        for r in recs:
+            fh.write(r)

@@ -1,0 +1,145 @@
+"""Mirror of python-core's Scan / Batch / Sequence (python-core/deciphon_core/scan.py:23-83,
+batch.py:8-33, sequence.py) over libdeciphon_b200.so -- same constructor arguments, same
+methods, same error type behaviour (a DeciphonError carrying the C error code)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdeciphon_b200.so")
+
+_CALLBACK = C.CFUNCTYPE(None, C.c_void_p)
+
+# every symbol include/deciphon_b200.h declares
+SYMBOLS = [
+    ("dcp_scan_new", C.c_void_p, []),
+    ("dcp_scan_del", None, [C.c_void_p]),
+    ("dcp_scan_setup", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_int, C.c_bool, C.c_bool, C.c_bool, _CALLBACK,
+                                 C.c_void_p]),
+    ("dcp_scan_run", C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    ("dcp_scan_interrupt", None, [C.c_void_p]),
+    ("dcp_scan_progress", C.c_int, [C.c_void_p]),
+    ("dcp_press_new", C.c_void_p, []),
+    ("dcp_press_setup", C.c_int, [C.c_void_p, C.c_int, C.c_float]),
+    ("dcp_press_open", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    ("dcp_press_nproteins", C.c_long, [C.c_void_p]),
+    ("dcp_press_next", C.c_int, [C.c_void_p]),
+    ("dcp_press_end", C.c_bool, [C.c_void_p]),
+    ("dcp_press_close", C.c_int, [C.c_void_p]),
+    ("dcp_press_del", None, [C.c_void_p]),
+    ("dcp_batch_new", C.c_void_p, []),
+    ("dcp_batch_del", None, [C.c_void_p]),
+    ("dcp_batch_add", C.c_int, [C.c_void_p, C.c_long, C.c_char_p, C.c_char_p]),
+    ("dcp_batch_reset", None, [C.c_void_p]),
+    ("dcp_error_string", C.c_char_p, [C.c_int]),
+    ("dcpb200_db_info", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_float)]),
+]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `make -C deciphon_b200/host`")
+    lib = C.CDLL(LIB_PATH)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+class DeciphonError(RuntimeError):
+    """python-core/deciphon_core/error.py:6-9: message via dcp_error_string."""
+
+    def __init__(self, errno: int):
+        self.errno = errno
+        super().__init__(lib.dcp_error_string(errno).decode())
+
+
+@dataclass
+class Sequence:
+    id: int
+    name: str
+    data: str
+
+
+class Batch:
+    def __init__(self):
+        self._cbatch = lib.dcp_batch_new()
+        if not self._cbatch:
+            raise MemoryError()
+
+    def add(self, sequence: Sequence):
+        if rc := lib.dcp_batch_add(self._cbatch, sequence.id, sequence.name.encode(), sequence.data.encode()):
+            raise DeciphonError(rc)
+
+    def reset(self):
+        lib.dcp_batch_reset(self._cbatch)
+
+    @property
+    def cdata(self):
+        return self._cbatch
+
+    def __del__(self):
+        if getattr(self, "_cbatch", None):
+            lib.dcp_batch_del(self._cbatch)
+            self._cbatch = None
+
+
+class Scan:
+    def __init__(self, dbfile, port: int, num_threads: int, multi_hits: bool, hmmer3_compat: bool, cache: bool):
+        self._cscan = lib.dcp_scan_new()
+        if not self._cscan:
+            raise MemoryError()
+        self.interrupted = False
+        self.callbacks = 0
+
+        def _cb(_userdata):
+            self.callbacks += 1
+
+        self._cb = _CALLBACK(_cb)  # keep alive
+        path = str(getattr(dbfile, "path", dbfile)).encode()
+        if rc := lib.dcp_scan_setup(self._cscan, path, port, num_threads, multi_hits, hmmer3_compat, cache, self._cb,
+                                    None):
+            lib.dcp_scan_del(self._cscan)
+            self._cscan = None
+            raise DeciphonError(rc)
+
+    def run(self, snap, batch: Batch):
+        """snap: a directory path or an object with .basedir (deciphon_schema.NewSnapFile)."""
+        self.interrupted = False
+        basedir = str(getattr(snap, "basedir", snap)).encode()
+        if rc := lib.dcp_scan_run(self._cscan, batch.cdata, basedir):
+            raise DeciphonError(rc)
+
+    def interrupt(self):
+        self.interrupted = True
+        lib.dcp_scan_interrupt(self._cscan)
+
+    def progress(self) -> int:
+        return lib.dcp_scan_progress(self._cscan)
+
+    def free(self):
+        if getattr(self, "_cscan", None):
+            lib.dcp_scan_del(self._cscan)
+            self._cscan = None
+
+    def __del__(self):
+        self.free()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *_):
+        self.free()
+
+
+def db_info(path: str):
+    n, total, eps = C.c_int(), C.c_long(), C.c_float()
+    if rc := lib.dcpb200_db_info(str(path).encode(), C.byref(n), C.byref(total), C.byref(eps)):
+        raise DeciphonError(rc)
+    return n.value, total.value, eps.value
