@@ -100,14 +100,24 @@ struct dcpgpu_ctx
   double last_cells = 0;
   int64_t launches = 0; // cumulative count of kernels this library launched
 
-  // trace pass state
+  // trace pass state (buffers grow on demand and are reused across calls)
   std::vector<Pair> t_pairs;
   Pair *d_tpairs = nullptr;
+  size_t tpairs_cap = 0;
   uint32_t *d_xnodes = nullptr;
+  size_t xnodes_cap = 0;
   uint16_t *d_nodes = nullptr;
+  size_t nodes_cap = 0;
   long long *d_xnode_off = nullptr, *d_node_off = nullptr, *d_step_off = nullptr;
+  size_t xnode_off_cap = 0, node_off_cap = 0, step_off_cap = 0;
   int *d_nsteps = nullptr;
+  size_t nsteps_cap = 0;
   float2 *d_tout = nullptr;
+  size_t tout_cap = 0;
+  uint16_t *d_step_ids = nullptr;
+  size_t step_ids_cap = 0;
+  uint8_t *d_step_sz = nullptr;
+  size_t step_sz_cap = 0;
   std::vector<long long> t_xnode_off, t_node_off;
   std::vector<int> t_nsteps;
   bool traced = false;
@@ -143,7 +153,7 @@ int ensure(dcpgpu_ctx *ctx, T *&ptr, size_t &cap, size_t need)
   if (ptr) CU(cudaFree(ptr));
   ptr = nullptr;
   cap = 0;
-  size_t n = std::max<size_t>(need, 16);
+  size_t n = std::max<size_t>(need + need / 4, 16); // head-room: sizes vary a little from call to call
   CU(cudaMalloc(reinterpret_cast<void **>(&ptr), n * sizeof(T)));
   cap = n;
   return 0;
@@ -542,6 +552,8 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_step_off);
   cudaFree(ctx->d_nsteps);
   cudaFree(ctx->d_tout);
+  cudaFree(ctx->d_step_ids);
+  cudaFree(ctx->d_step_sz);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1014,21 +1026,14 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     ctx->t_xnode_off[(size_t)i + 1] = ctx->t_xnode_off[(size_t)i] + (pairs[i].len + 1);
     ctx->t_node_off[(size_t)i + 1] = ctx->t_node_off[(size_t)i] + (long long)(pairs[i].len + 1) * K;
   }
-  cudaFree(ctx->d_tpairs); ctx->d_tpairs = nullptr;
-  cudaFree(ctx->d_xnodes); ctx->d_xnodes = nullptr;
-  cudaFree(ctx->d_nodes); ctx->d_nodes = nullptr;
-  cudaFree(ctx->d_xnode_off); ctx->d_xnode_off = nullptr;
-  cudaFree(ctx->d_node_off); ctx->d_node_off = nullptr;
-  cudaFree(ctx->d_nsteps); ctx->d_nsteps = nullptr;
-  cudaFree(ctx->d_tout); ctx->d_tout = nullptr;
   size_t const n = (size_t)npairs;
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tpairs), n * sizeof(Pair)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xnodes), (size_t)ctx->t_xnode_off[n] * sizeof(uint32_t)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_nodes), (size_t)ctx->t_node_off[n] * sizeof(uint16_t)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xnode_off), (n + 1) * sizeof(long long)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_node_off), (n + 1) * sizeof(long long)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_nsteps), n * sizeof(int)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_tout), n * sizeof(float2)));
+  if ((rc = ensure(ctx, ctx->d_tpairs, ctx->tpairs_cap, n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_xnodes, ctx->xnodes_cap, (size_t)ctx->t_xnode_off[n]))) return rc;
+  if ((rc = ensure(ctx, ctx->d_nodes, ctx->nodes_cap, (size_t)ctx->t_node_off[n]))) return rc;
+  if ((rc = ensure(ctx, ctx->d_xnode_off, ctx->xnode_off_cap, n + 1))) return rc;
+  if ((rc = ensure(ctx, ctx->d_node_off, ctx->node_off_cap, n + 1))) return rc;
+  if ((rc = ensure(ctx, ctx->d_nsteps, ctx->nsteps_cap, n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_tout, ctx->tout_cap, n))) return rc;
   CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -1076,13 +1081,13 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
   std::vector<long long> off(n + 1, 0);
   for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + ctx->t_nsteps[i];
   size_t const total = (size_t)off[n];
-  uint16_t *d_ids = nullptr;
-  uint8_t *d_sz = nullptr;
-  cudaFree(ctx->d_step_off); ctx->d_step_off = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_step_off), (n + 1) * sizeof(long long)));
-  CU(cudaMalloc(reinterpret_cast<void **>(&d_ids), total * sizeof(uint16_t)));
-  cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&d_sz), total);
-  if (e != cudaSuccess) { cudaFree(d_ids); return fail_cuda(ctx, e, "cudaMalloc(steps)"); }
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_step_off, ctx->step_off_cap, n + 1))) return rc;
+  if ((rc = ensure(ctx, ctx->d_step_ids, ctx->step_ids_cap, total))) return rc;
+  if ((rc = ensure(ctx, ctx->d_step_sz, ctx->step_sz_cap, total))) return rc;
+  uint16_t *d_ids = ctx->d_step_ids;
+  uint8_t *d_sz = ctx->d_step_sz;
+  cudaError_t e;
   std::vector<uint16_t> h_ids(total);
   std::vector<uint8_t> h_sz(total);
   e = cudaMemcpyAsync(ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
@@ -1107,8 +1112,6 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_ids);
-  cudaFree(d_sz);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "trace_fetch");
   for (size_t i = 0; i < n; ++i)
   {

@@ -197,6 +197,9 @@ struct ScoreCfg
   // Long-code rows through the TMA ring?  Measured on B200 (profiles/): CTA-wide bulk copies
   // (W > 1, 2..8 KB each) beat per-lane loads, 1 KB per-warp copies (W = 1) do not.
   static constexpr bool TMA_RING = W > 1;
+  // W = 1: software-pipelined rows (next row's t = 2..5 accumulation in the shadow of the
+  // delete-chain sweeps)
+  static constexpr bool PIPELINED = W == 1;
 };
 
 template <int Q>
@@ -431,6 +434,94 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q
     s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
 }
 
+
+// ---- software-pipelined single-warp row (W = 1) ------------------------------------------------
+// Row l+1's accumulation over the emission lengths t = 2..5 reads only rows l-1..l-4, so it does
+// not depend on anything row l computes.  It is issued in the shadow of row l's serial tail (the
+// delete-chain sweeps, whose dependent FADD/FMNMX chain would otherwise leave the issue slots
+// idle), and its loads are in flight during the first sweep.  Row l then only has to add the
+// one-nucleotide term (which needs P(l-1)) before its own delete chain starts.
+template <int Q, int J>
+__device__ __forceinline__ void dp_row_pipe(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q], float &xp,
+                                            ProfileDesc const &pd, unsigned hist, unsigned hist1, int lane,
+                                            float NB, float EB, float JB, float &E, float &x)
+{
+  constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
+  int const Kpad = pd.Kpad;
+
+  // (A) finish row l: the t = 1 term needs P(l-1), Q(l-1)
+  float M[Q], I[Q];
+  float xacc;
+  {
+    int const c1 = hist & 3;
+    float2 const nb = __ldg(pd.nulbg + c1);
+    float e[Q];
+    load_chunks<Q, 32>(e, pd.em + (size_t)c1 * Kpad, lane);
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+    {
+      M[q] = fminf(Mp[q], s.P[s1][q] + e[q]);
+      I[q] = fminf(Ip[q], s.Qv[s1][q] + nb.y);
+    }
+    xacc = fminf(xp, s.px[s1] + nb.x);
+  }
+
+  // loads of row l+1's emission rows for t = 2..5
+  int const c2 = 4 + (hist1 & 15), c3 = 20 + (hist1 & 63), c4 = 84 + (hist1 & 255), c5 = 340 + (hist1 & 1023);
+  float2 const nb2 = __ldg(pd.nulbg + c2), nb3 = __ldg(pd.nulbg + c3), nb4 = __ldg(pd.nulbg + c4),
+               nb5 = __ldg(pd.nulbg + c5);
+  float e2[Q], e3[Q], e4[Q], e5[Q];
+  load_chunks<Q, 32>(e2, pd.em + (size_t)c2 * Kpad, lane);
+  load_chunks<Q, 32>(e3, pd.em + (size_t)c3 * Kpad, lane);
+  load_chunks<Q, 32>(e4, pd.em + (size_t)c4 * Kpad, lane);
+  load_chunks<Q, 32>(e5, pd.em + (size_t)c5 * Kpad, lane);
+
+  // delete chain of row l: source terms + first sweep (viterbi.c:538, 552-567)
+  float const mprev = __shfl_up_sync(FULL_MASK, M[Q - 1], 1);
+  float const iprev = __shfl_up_sync(FULL_MASK, I[Q - 1], 1);
+  float D[Q];
+  D[0] = mprev + s.MD[0];
+#pragma unroll
+  for (int q = 1; q < Q; ++q)
+    D[q] = M[q - 1] + s.MD[q];
+  {
+    float const din0 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
+    D[0] = fminf(D[0], din0 + s.DD[0]);
+    d_sweep<Q>(s, D);
+  }
+
+  // row l+1, t = 2..5: rows l-1, l-2, l-3, l-4 are ring slots s1..s4 of THIS row
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+  {
+    Mp[q] = fminf(min3(s.P[s1][q] + e2[q], s.P[s2][q] + e3[q], s.P[s3][q] + e4[q]), s.P[s4][q] + e5[q]);
+    Ip[q] = fminf(min3(s.Qv[s1][q] + nb2.y, s.Qv[s2][q] + nb3.y, s.Qv[s3][q] + nb4.y), s.Qv[s4][q] + nb5.y);
+  }
+  xp = fminf(min3(s.px[s1] + nb2.x, s.px[s2] + nb3.x, s.px[s3] + nb4.x), s.px[s4] + nb5.x);
+
+  // second sweep unconditionally (measured: one extra sweep per row on average), then lazy
+  {
+    float const din1 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
+    D[0] = fminf(D[0], din1 + s.DD[0]);
+    d_sweep<Q>(s, D);
+  }
+  float const dprev = d_lazy<Q>(s, D, false);
+
+  E = e_partial<Q>(M, D);
+  x = xacc;
+  float const N = __shfl_sync(FULL_MASK, x, 0);
+  float const Jv = __shfl_sync(FULL_MASK, x, 1);
+  float const B = min3(N + NB, E + EB, Jv + JB);
+  s.px[J] = fminf(E + s.xa, x + s.xb);
+  s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
+#pragma unroll
+  for (int q = 1; q < Q; ++q)
+    s.P[J][q] = fminf(min3(B + s.BM[q], M[q - 1] + s.MM[q], I[q - 1] + s.IM[q]), D[q - 1] + s.DM[q]);
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+    s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
+}
+
 template <int Q, int W>
 __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> const &ring, unsigned &phase,
                                           uint32_t const *__restrict__ words, int start, int L,
@@ -503,6 +594,36 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
   }
   float E = CUDART_INF_F, x = CUDART_INF_F;
 
+  if constexpr (ScoreCfg<W>::PIPELINED)
+  {
+    // partial accumulators of the next row (t = 2..5); row 1 has no such predecessors
+    float Mp[Q], Ip[Q], xp = CUDART_INF_F;
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+    {
+      Mp[q] = CUDART_INF_F;
+      Ip[q] = CUDART_INF_F;
+    }
+#define DCP_ROWP(JJ_)                                                                            \
+  {                                                                                              \
+    if (l > L) break;                                                                            \
+    DCP_NEXT_NT()                                                                                \
+    dp_row_pipe<Q, JJ_>(s, Mp, Ip, xp, pd, H >> 10, (H >> 8) & 1023u, lane, NB, EB, JB, E, x);   \
+    ++l;                                                                                         \
+  }
+    int l = 1;
+    for (;;)
+    {
+      DCP_ROWP(1)
+      DCP_ROWP(2)
+      DCP_ROWP(3)
+      DCP_ROWP(4)
+      DCP_ROWP(0)
+    }
+#undef DCP_ROWP
+  }
+  else
+  {
 #define DCP_ROW(JJ_)                                                                             \
   {                                                                                              \
     if (l > L) break;                                                                            \
@@ -511,16 +632,17 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
                       l & 1, E, x);                                                              \
     ++l;                                                                                         \
   }
-  int l = 1;
-  for (;;)
-  {
-    DCP_ROW(1)
-    DCP_ROW(2)
-    DCP_ROW(3)
-    DCP_ROW(4)
-    DCP_ROW(0)
-  }
+    int l = 1;
+    for (;;)
+    {
+      DCP_ROW(1)
+      DCP_ROW(2)
+      DCP_ROW(3)
+      DCP_ROW(4)
+      DCP_ROW(0)
+    }
 #undef DCP_ROW
+  }
 #undef DCP_NEXT_NT
 
   float const C = __shfl_sync(FULL_MASK, x, 2);
