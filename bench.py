@@ -265,8 +265,8 @@ def run_b200(args, rank, local_rank, world):
         stats["score_ms"] += dev.last_kernel_ms()
         stats["cells"] += dev.last_cells()
         if len(pr):
-            _, paths = dev.trace_pairs(pr, True, False)
-            stats["steps"] += sum(len(a) for a, _ in paths)
+            _, off, _ids, _sz = dev.trace_pairs_flat(pr, True, False)
+            stats["steps"] += int(off[-1])
         stats["hits"] += len(pr)
 
     # ---- phase 1: reads resident in HBM ("value") ----
@@ -307,8 +307,8 @@ def run_b200(args, rank, local_rank, world):
         pr = hit_pairs(0)
         nst = 0
         if len(pr):
-            _, paths = dev.trace_pairs(pr, True, False)
-            nst = sum(len(a) for a, _ in paths)
+            _, off, _ids, _sz = dev.trace_pairs_flat(pr, True, False)
+            nst = int(off[-1])
         h2d = (R * L + 3) // 4 + R * 12 + len(pr) * 16
         d2h = nprof * R * 8 + len(pr) * 8 + nst * 3
         return float(nul[0]) + float(alt[-1])

@@ -139,6 +139,49 @@ __device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restri
   if constexpr ((Q & 1) != 0) e[Q - 1] = __ldg(row + VL * (Q - 1) + vl);
 }
 
+// Per-lane base pointers into a profile's emission table: a code row is then reached with ONE
+// 32-bit byte offset (code * 4*Kpad < 2^32) added to a 64-bit base, instead of a 64-bit
+// multiply-add per access.
+template <int Q, int VL>
+struct RowBase
+{
+  char const *b4; // first float4 chunk of this lane
+  char const *b2; // the float2 chunk (Q & 2)
+  char const *b1; // the scalar chunk (Q & 1)
+  __device__ __forceinline__ RowBase(float const *em, int vl)
+  {
+    constexpr int N4 = Q / 4;
+    b4 = reinterpret_cast<char const *>(em) + (size_t)vl * 16;
+    b2 = reinterpret_cast<char const *>(em + VL * (N4 * 4)) + (size_t)vl * 8;
+    b1 = reinterpret_cast<char const *>(em + VL * (Q - 1)) + (size_t)vl * 4;
+  }
+  __device__ __forceinline__ void load(float (&e)[Q], uint32_t byte_off) const
+  {
+    constexpr int N4 = Q / 4;
+#pragma unroll
+    for (int c = 0; c < N4; ++c)
+    {
+      float4 v = __ldg(reinterpret_cast<float4 const *>(b4 + byte_off + c * 16 * VL));
+      e[4 * c + 0] = v.x;
+      e[4 * c + 1] = v.y;
+      e[4 * c + 2] = v.z;
+      e[4 * c + 3] = v.w;
+    }
+    if constexpr ((Q & 2) != 0)
+    {
+      float2 v = __ldg(reinterpret_cast<float2 const *>(b2 + byte_off));
+      e[N4 * 4 + 0] = v.x;
+      e[N4 * 4 + 1] = v.y;
+    }
+    if constexpr ((Q & 1) != 0) e[Q - 1] = __ldg(reinterpret_cast<float const *>(b1 + byte_off));
+  }
+};
+
+__device__ __forceinline__ float2 ldg_nulbg(float2 const *nulbg, int code)
+{
+  return __ldg(reinterpret_cast<float2 const *>(reinterpret_cast<char const *>(nulbg) + (uint32_t)code * 8u));
+}
+
 // Same row layout, read from a TMA-filled shared-memory stage (conflict-free LDS.128/64/32).
 template <int Q, int VL>
 __device__ __forceinline__ void load_chunks_smem(float (&e)[Q], float const *row, int vl)
@@ -447,16 +490,17 @@ __device__ __forceinline__ void dp_row_pipe(Lane<Q> &s, float (&Mp)[Q], float (&
                                             float NB, float EB, float JB, float &E, float &x)
 {
   constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
-  int const Kpad = pd.Kpad;
+  uint32_t const rowb = (uint32_t)pd.Kpad * 4u; // bytes per code row
+  RowBase<Q, 32> const rb(pd.em, lane);
 
   // (A) finish row l: the t = 1 term needs P(l-1), Q(l-1)
   float M[Q], I[Q];
   float xacc;
   {
     int const c1 = hist & 3;
-    float2 const nb = __ldg(pd.nulbg + c1);
+    float2 const nb = ldg_nulbg(pd.nulbg, c1);
     float e[Q];
-    load_chunks<Q, 32>(e, pd.em + (size_t)c1 * Kpad, lane);
+    rb.load(e, (uint32_t)c1 * rowb);
 #pragma unroll
     for (int q = 0; q < Q; ++q)
     {
@@ -468,13 +512,13 @@ __device__ __forceinline__ void dp_row_pipe(Lane<Q> &s, float (&Mp)[Q], float (&
 
   // loads of row l+1's emission rows for t = 2..5
   int const c2 = 4 + (hist1 & 15), c3 = 20 + (hist1 & 63), c4 = 84 + (hist1 & 255), c5 = 340 + (hist1 & 1023);
-  float2 const nb2 = __ldg(pd.nulbg + c2), nb3 = __ldg(pd.nulbg + c3), nb4 = __ldg(pd.nulbg + c4),
-               nb5 = __ldg(pd.nulbg + c5);
+  float2 const nb2 = ldg_nulbg(pd.nulbg, c2), nb3 = ldg_nulbg(pd.nulbg, c3), nb4 = ldg_nulbg(pd.nulbg, c4),
+               nb5 = ldg_nulbg(pd.nulbg, c5);
   float e2[Q], e3[Q], e4[Q], e5[Q];
-  load_chunks<Q, 32>(e2, pd.em + (size_t)c2 * Kpad, lane);
-  load_chunks<Q, 32>(e3, pd.em + (size_t)c3 * Kpad, lane);
-  load_chunks<Q, 32>(e4, pd.em + (size_t)c4 * Kpad, lane);
-  load_chunks<Q, 32>(e5, pd.em + (size_t)c5 * Kpad, lane);
+  rb.load(e2, (uint32_t)c2 * rowb);
+  rb.load(e3, (uint32_t)c3 * rowb);
+  rb.load(e4, (uint32_t)c4 * rowb);
+  rb.load(e5, (uint32_t)c5 * rowb);
 
   // delete chain of row l: source terms + first sweep (viterbi.c:538, 552-567)
   float const mprev = __shfl_up_sync(FULL_MASK, M[Q - 1], 1);

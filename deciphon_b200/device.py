@@ -177,6 +177,23 @@ class Device:
         return v.value
 
     # -- trace pass ----------------------------------------------------------------------
+    def trace_pairs_flat(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):
+        """Returns (alt_cost[n], offsets[n+1], state_ids uint16[total], seqsizes uint8[total])."""
+        pairs = np.ascontiguousarray(pairs)
+        if pairs.dtype != PAIR_DTYPE:
+            pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4).view(PAIR_DTYPE).reshape(-1)
+        n = pairs.shape[0]
+        alt = np.empty(n, dtype=np.float32)
+        nsteps = np.zeros(n, dtype=np.int32)
+        self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs), flags_of(multi_hits, hmmer3_compat),
+                                           _ptr(alt), _ptr(nsteps)))
+        off = np.zeros(n + 1, dtype=np.int64)
+        off[1:] = np.cumsum(nsteps)
+        ids = np.zeros(max(int(off[-1]), 1), dtype=np.uint16)
+        sz = np.zeros(max(int(off[-1]), 1), dtype=np.uint8)
+        self._check(lib.dcpgpu_trace_fetch(self._h, _ptr(off), _ptr(ids), _ptr(sz)))
+        return alt, off, ids, sz
+
     def trace_pairs(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):
         """Returns (alt_cost[n], paths) with paths[i] = (state_ids uint16[], seqsizes uint8[])."""
         pairs = np.ascontiguousarray(pairs)
