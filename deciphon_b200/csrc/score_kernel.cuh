@@ -240,9 +240,6 @@ struct ScoreCfg
   // Long-code rows through the TMA ring?  Measured on B200 (profiles/): CTA-wide bulk copies
   // (W > 1, 2..8 KB each) beat per-lane loads, 1 KB per-warp copies (W = 1) do not.
   static constexpr bool TMA_RING = W > 1;
-  // W = 1: software-pipelined rows (next row's t = 2..5 accumulation in the shadow of the
-  // delete-chain sweeps)
-  static constexpr bool PIPELINED = W == 1;
 };
 
 template <int Q>
@@ -293,87 +290,77 @@ __device__ __forceinline__ float e_partial(float const (&M)[Q], float const (&D)
   return warp_min_nonneg(e);
 }
 
-// One DP row l (J = l % 5).  hist = last five nucleotides ending at l-1, 2 bits each.
+// One software-pipelined DP row l (J = l % 5).
+//
+// Row l+1's accumulation over the emission lengths t = 2..5 reads only rows l-1..l-4, so it does
+// not depend on anything row l computes.  It is issued in the shadow of row l's serial tail (the
+// delete-chain sweeps, whose dependent FADD/FMNMX chain would otherwise leave the issue slots
+// idle); row l itself then only has to add the one-nucleotide term (which needs P(l-1)) to the
+// partial accumulators Mp/Ip/xp it inherits before its own delete chain starts.
+//   hist  = the five nucleotides ending at l-1 (codes of row l), hist1 = ending at l (row l+1),
+//   hist6 = ending at l+5 (row l+6: its long-code rows are requested from the TMA ring now).
 template <int Q, int W, int J>
-__device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q, W> const &ring, unsigned hist,
-                                       unsigned hist_ahead, bool refill, unsigned &phase, int lane, int warp,
-                                       float NB, float EB, float JB, Mail *mail, int volatile *flags, int par,
-                                       float &E, float &x)
+__device__ __forceinline__ void dp_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q], float &xp, ProfileDesc const &pd,
+                                       Ring<Q, W> const &ring, unsigned hist, unsigned hist1, unsigned hist6,
+                                       bool have_next, bool refill, unsigned &phase, int lane, int warp, float NB,
+                                       float EB, float JB, Mail *mail, int volatile *flags, int par, float &E,
+                                       float &x)
 {
   constexpr int VL = 32 * W;
+  constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
+  constexpr int JN = (J + 1) % 5; // ring slot of DP row l+1
   int const vl = warp * 32 + lane;
-  int code[5];
-  code[0] = hist & 3;
-  code[1] = 4 + (hist & 15);
-  code[2] = 20 + (hist & 63);
-  code[3] = 84 + (hist & 255);
-  code[4] = 340 + (hist & 1023);
-  constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5, s5 = J;
+  uint32_t const rowb = (uint32_t)pd.Kpad * 4u; // bytes per code row
+  RowBase<Q, VL> const rb(pd.em, vl);
 
-  // M_k(l), I_k(l) and the special-state recurrences: min over the five emission lengths
+  // (A) finish row l: the t = 1 term needs P(l-1), Q(l-1)
   float M[Q], I[Q];
   float xacc;
   {
-    float2 const nb = __ldg(pd.nulbg + code[0]);
+    int const c1 = hist & 3;
+    float2 const nb = ldg_nulbg(pd.nulbg, c1);
     float e[Q];
-    load_chunks<Q, VL>(e, pd.em + (size_t)code[0] * pd.Kpad, vl);
+    rb.load(e, (uint32_t)c1 * rowb);
 #pragma unroll
     for (int q = 0; q < Q; ++q)
     {
-      M[q] = s.P[s1][q] + e[q];
-      I[q] = s.Qv[s1][q] + nb.y;
+      M[q] = fminf(Mp[q], s.P[s1][q] + e[q]);
+      I[q] = fminf(Ip[q], s.Qv[s1][q] + nb.y);
     }
-    xacc = s.px[s1] + nb.x;
-  }
-  {
-    float2 const nb2 = __ldg(pd.nulbg + code[1]);
-    float2 const nb3 = __ldg(pd.nulbg + code[2]);
-    float e2[Q], e3[Q];
-    load_chunks<Q, VL>(e2, pd.em + (size_t)code[1] * pd.Kpad, vl);
-    load_chunks<Q, VL>(e3, pd.em + (size_t)code[2] * pd.Kpad, vl);
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      M[q] = min3(M[q], s.P[s2][q] + e2[q], s.P[s3][q] + e3[q]);
-      I[q] = min3(I[q], s.Qv[s2][q] + nb2.y, s.Qv[s3][q] + nb3.y);
-    }
-    xacc = min3(xacc, s.px[s2] + nb2.x, s.px[s3] + nb3.x);
-  }
-  {
-    float2 const nb4 = __ldg(pd.nulbg + code[3]);
-    float2 const nb5 = __ldg(pd.nulbg + code[4]);
-    float e4[Q], e5[Q];
-    if constexpr (ScoreCfg<W>::TMA_RING)
-    { // the 4- and 5-mer rows of this DP row were requested five rows ago
-      tma::mbar_wait(ring.bar_addr + 8u * J, (phase >> J) & 1u);
-      phase ^= 1u << J;
-      load_chunks_smem<Q, VL>(e4, ring.stage + (J * 2 + 0) * Ring<Q, W>::ROW, vl);
-      load_chunks_smem<Q, VL>(e5, ring.stage + (J * 2 + 1) * Ring<Q, W>::ROW, vl);
-    }
-    else
-    {
-      load_chunks<Q, VL>(e4, pd.em + (size_t)code[3] * pd.Kpad, vl);
-      load_chunks<Q, VL>(e5, pd.em + (size_t)code[4] * pd.Kpad, vl);
-    }
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      M[q] = min3(M[q], s.P[s4][q] + e4[q], s.P[s5][q] + e5[q]);
-      I[q] = min3(I[q], s.Qv[s4][q] + nb4.y, s.Qv[s5][q] + nb5.y);
-    }
-    xacc = min3(xacc, s.px[s4] + nb4.x, s.px[s5] + nb5.x);
-  }
-  if constexpr (W == 1 && ScoreCfg<W>::TMA_RING)
-  { // slot J is consumed: request row l+5 into it (one elected lane drives the TMA)
-    if (refill && lane == 0) ring.fill(pd, J, hist_ahead);
+    xacc = fminf(xp, s.px[s1] + nb.x);
   }
 
-  // Delete chain (viterbi.c:538, 552-580).  Lane 0 of the first warp is node 0, whose
-  // incoming transitions are +INF (protein.c:366-370), so the wrapped shuffle value is inert.
+  // emission rows of row l+1 for t = 2..5
+  int const c2 = 4 + (hist1 & 15), c3 = 20 + (hist1 & 63), c4 = 84 + (hist1 & 255), c5 = 340 + (hist1 & 1023);
+  float2 const nb2 = ldg_nulbg(pd.nulbg, c2), nb3 = ldg_nulbg(pd.nulbg, c3), nb4 = ldg_nulbg(pd.nulbg, c4),
+               nb5 = ldg_nulbg(pd.nulbg, c5);
+  float e2[Q], e3[Q], e4[Q], e5[Q];
+  rb.load(e2, (uint32_t)c2 * rowb);
+  rb.load(e3, (uint32_t)c3 * rowb);
+  if constexpr (ScoreCfg<W>::TMA_RING)
+  { // the 4- and 5-mer rows of DP row l+1 were requested by TMA five rows ago
+    if (have_next)
+    {
+      tma::mbar_wait(ring.bar_addr + 8u * JN, (phase >> JN) & 1u);
+      phase ^= 1u << JN;
+    }
+    load_chunks_smem<Q, VL>(e4, ring.stage + (JN * 2 + 0) * Ring<Q, W>::ROW, vl);
+    load_chunks_smem<Q, VL>(e5, ring.stage + (JN * 2 + 1) * Ring<Q, W>::ROW, vl);
+  }
+  else
+  {
+    rb.load(e4, (uint32_t)c4 * rowb);
+    rb.load(e5, (uint32_t)c5 * rowb);
+  }
+
+  // Delete chain of row l: source terms + first sweep (viterbi.c:538, 552-567).  Lane 0 of the
+  // first warp is node 0, whose incoming transitions are +INF (protein.c:366-370), so the
+  // wrapped shuffle value is inert there; lane 0 of a later warp gets its predecessor through
+  // the mailbox below.
   bool const head = W > 1 && lane == 0 && warp > 0;
   float mprev = __shfl_up_sync(FULL_MASK, M[Q - 1], 1);
   float iprev = __shfl_up_sync(FULL_MASK, I[Q - 1], 1);
-  if (head) mprev = CUDART_INF_F; // arrives through the mailbox below
+  if (head) mprev = CUDART_INF_F;
   float D[Q];
   D[0] = mprev + s.MD[0];
 #pragma unroll
@@ -383,6 +370,23 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q
     float din0 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
     if (head) din0 = CUDART_INF_F;
     D[0] = fminf(D[0], din0 + s.DD[0]);
+    d_sweep<Q>(s, D);
+  }
+
+  // row l+1, t = 2..5: rows l-1, l-2, l-3, l-4 are ring slots s1..s4 of THIS row
+#pragma unroll
+  for (int q = 0; q < Q; ++q)
+  {
+    Mp[q] = fminf(min3(s.P[s1][q] + e2[q], s.P[s2][q] + e3[q], s.P[s3][q] + e4[q]), s.P[s4][q] + e5[q]);
+    Ip[q] = fminf(min3(s.Qv[s1][q] + nb2.y, s.Qv[s2][q] + nb3.y, s.Qv[s3][q] + nb4.y), s.Qv[s4][q] + nb5.y);
+  }
+  xp = fminf(min3(s.px[s1] + nb2.x, s.px[s2] + nb3.x, s.px[s3] + nb4.x), s.px[s4] + nb5.x);
+
+  // second sweep unconditionally (measured: one extra sweep per row on average), then lazy
+  {
+    float din1 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
+    if (head) din1 = CUDART_INF_F;
+    D[0] = fminf(D[0], din1 + s.DD[0]);
     d_sweep<Q>(s, D);
   }
   float dprev = d_lazy<Q>(s, D, head);
@@ -395,8 +399,8 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q
     Mail *box = mail + par * W;
     if (lane == 31) box[warp] = Mail{M[Q - 1], I[Q - 1], D[Q - 1], e};
     __syncthreads();
-    // every warp has consumed ring slot J: request row l+5 into it
-    if (ScoreCfg<W>::TMA_RING && refill && threadIdx.x == 0) ring.fill(pd, J, hist_ahead);
+    // every warp has consumed ring slot JN (row l+1): request row l+6 into it
+    if (ScoreCfg<W>::TMA_RING && refill && threadIdx.x == 0) ring.fill(pd, JN, hist6);
     if (warp > 0)
     {
       Mail const pm = box[warp - 1];
@@ -413,14 +417,14 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q
         D[0] = fminf(D[0], c);
         d_sweep<Q>(s, D);
         d_lazy<Q>(s, D, head);
-        float const e2 = e_partial<Q>(M, D);
-        if (lane == 31 && (D[Q - 1] != dlast || e2 != e))
+        float const e2n = e_partial<Q>(M, D);
+        if (lane == 31 && (D[Q - 1] != dlast || e2n != e))
         {
           box[warp].D = D[Q - 1];
-          box[warp].E = e2;
+          box[warp].E = e2n;
           flags[par] = 1;
         }
-        e = e2;
+        e = e2n;
       }
     }
     for (;;)
@@ -440,14 +444,14 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q
           D[0] = fminf(D[0], c);
           d_sweep<Q>(s, D);
           d_lazy<Q>(s, D, head);
-          float const e2 = e_partial<Q>(M, D);
-          if (lane == 31 && (D[Q - 1] != dlast || e2 != e))
+          float const e2n = e_partial<Q>(M, D);
+          if (lane == 31 && (D[Q - 1] != dlast || e2n != e))
           {
             box[warp].D = D[Q - 1];
-            box[warp].E = e2;
+            box[warp].E = e2n;
             flags[par] = 1;
           }
-          e = e2;
+          e = e2n;
         }
       }
     }
@@ -468,95 +472,6 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, ProfileDesc const &pd, Ring<Q
   s.px[J] = fminf(E + s.xa, x + s.xb);
 
   // P(l), Q(l) into the slot that held row l-5
-  s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    s.P[J][q] = fminf(min3(B + s.BM[q], M[q - 1] + s.MM[q], I[q - 1] + s.IM[q]), D[q - 1] + s.DM[q]);
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-    s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
-}
-
-
-// ---- software-pipelined single-warp row (W = 1) ------------------------------------------------
-// Row l+1's accumulation over the emission lengths t = 2..5 reads only rows l-1..l-4, so it does
-// not depend on anything row l computes.  It is issued in the shadow of row l's serial tail (the
-// delete-chain sweeps, whose dependent FADD/FMNMX chain would otherwise leave the issue slots
-// idle), and its loads are in flight during the first sweep.  Row l then only has to add the
-// one-nucleotide term (which needs P(l-1)) before its own delete chain starts.
-template <int Q, int J>
-__device__ __forceinline__ void dp_row_pipe(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q], float &xp,
-                                            ProfileDesc const &pd, unsigned hist, unsigned hist1, int lane,
-                                            float NB, float EB, float JB, float &E, float &x)
-{
-  constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
-  uint32_t const rowb = (uint32_t)pd.Kpad * 4u; // bytes per code row
-  RowBase<Q, 32> const rb(pd.em, lane);
-
-  // (A) finish row l: the t = 1 term needs P(l-1), Q(l-1)
-  float M[Q], I[Q];
-  float xacc;
-  {
-    int const c1 = hist & 3;
-    float2 const nb = ldg_nulbg(pd.nulbg, c1);
-    float e[Q];
-    rb.load(e, (uint32_t)c1 * rowb);
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      M[q] = fminf(Mp[q], s.P[s1][q] + e[q]);
-      I[q] = fminf(Ip[q], s.Qv[s1][q] + nb.y);
-    }
-    xacc = fminf(xp, s.px[s1] + nb.x);
-  }
-
-  // loads of row l+1's emission rows for t = 2..5
-  int const c2 = 4 + (hist1 & 15), c3 = 20 + (hist1 & 63), c4 = 84 + (hist1 & 255), c5 = 340 + (hist1 & 1023);
-  float2 const nb2 = ldg_nulbg(pd.nulbg, c2), nb3 = ldg_nulbg(pd.nulbg, c3), nb4 = ldg_nulbg(pd.nulbg, c4),
-               nb5 = ldg_nulbg(pd.nulbg, c5);
-  float e2[Q], e3[Q], e4[Q], e5[Q];
-  rb.load(e2, (uint32_t)c2 * rowb);
-  rb.load(e3, (uint32_t)c3 * rowb);
-  rb.load(e4, (uint32_t)c4 * rowb);
-  rb.load(e5, (uint32_t)c5 * rowb);
-
-  // delete chain of row l: source terms + first sweep (viterbi.c:538, 552-567)
-  float const mprev = __shfl_up_sync(FULL_MASK, M[Q - 1], 1);
-  float const iprev = __shfl_up_sync(FULL_MASK, I[Q - 1], 1);
-  float D[Q];
-  D[0] = mprev + s.MD[0];
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    D[q] = M[q - 1] + s.MD[q];
-  {
-    float const din0 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
-    D[0] = fminf(D[0], din0 + s.DD[0]);
-    d_sweep<Q>(s, D);
-  }
-
-  // row l+1, t = 2..5: rows l-1, l-2, l-3, l-4 are ring slots s1..s4 of THIS row
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-  {
-    Mp[q] = fminf(min3(s.P[s1][q] + e2[q], s.P[s2][q] + e3[q], s.P[s3][q] + e4[q]), s.P[s4][q] + e5[q]);
-    Ip[q] = fminf(min3(s.Qv[s1][q] + nb2.y, s.Qv[s2][q] + nb3.y, s.Qv[s3][q] + nb4.y), s.Qv[s4][q] + nb5.y);
-  }
-  xp = fminf(min3(s.px[s1] + nb2.x, s.px[s2] + nb3.x, s.px[s3] + nb4.x), s.px[s4] + nb5.x);
-
-  // second sweep unconditionally (measured: one extra sweep per row on average), then lazy
-  {
-    float const din1 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
-    D[0] = fminf(D[0], din1 + s.DD[0]);
-    d_sweep<Q>(s, D);
-  }
-  float const dprev = d_lazy<Q>(s, D, false);
-
-  E = e_partial<Q>(M, D);
-  x = xacc;
-  float const N = __shfl_sync(FULL_MASK, x, 0);
-  float const Jv = __shfl_sync(FULL_MASK, x, 1);
-  float const B = min3(N + NB, E + EB, Jv + JB);
-  s.px[J] = fminf(E + s.xa, x + s.xb);
   s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
 #pragma unroll
   for (int q = 1; q < Q; ++q)
@@ -608,9 +523,9 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
   s.xb = lane == 0 ? NN : lane == 1 ? JJ : lane == 2 ? CC : lane == 3 ? RR : CUDART_INF_F;
   s.px[0] = lane == 0 ? (0.0f + SN) : lane == 3 ? ((-RR) + RR) : CUDART_INF_F;
 
-  // Nucleotide stream, running five positions ahead of the DP row: H holds the last ten
-  // nucleotides, bits 10..19 = the five ending at l-1 (this row's codes), bits 0..9 = the five
-  // ending at l+4 (the codes of row l+5, whose long-code rows are requested now).
+  // Nucleotide stream, running six positions ahead of the DP row: H holds the last eleven
+  // nucleotides; at row l bits 12..21 = the five ending at l-1 (codes of row l), bits 10..19 =
+  // ending at l (row l+1), bits 0..9 = ending at l+5 (row l+6, requested from the TMA ring).
   int g = start;
   uint32_t const *wp = words + (g >> 4);
   uint32_t word = __ldg(wp) >> (2 * (g & 15));
@@ -618,7 +533,7 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
   unsigned H = 0;
 #define DCP_NEXT_NT()                                                                            \
   {                                                                                              \
-    H = ((H << 2) | (word & 3u)) & 0xFFFFFu;                                                     \
+    H = ((H << 2) | (word & 3u)) & 0x3FFFFFu;                                                    \
     word >>= 2;                                                                                  \
     if (--left == 0)                                                                             \
     {                                                                                            \
@@ -627,66 +542,44 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
     }                                                                                            \
   }
 #pragma unroll
-  for (int i = 0; i < 5; ++i)
+  for (int i = 0; i < 6; ++i)
     DCP_NEXT_NT()
-  // prologue: rows 1..5 (slots 1,2,3,4,0); row r ends at nucleotide r-1
-  if (ScoreCfg<W>::TMA_RING && (W == 1 ? lane : (int)threadIdx.x) == 0)
+  // prologue: long-code rows of DP rows 2..6 (ring slots 2,3,4,0,1); row r ends at nucleotide r-1.
+  // Row 1 has no predecessors for t >= 2, so its slot is never read and never filled.
+  if (ScoreCfg<W>::TMA_RING && threadIdx.x == 0)
   {
 #pragma unroll
-    for (int r = 1; r <= 5; ++r)
-      if (r <= L) ring.fill(pd, r % 5, H >> (2 * (5 - r)));
+    for (int r = 2; r <= 6; ++r)
+      if (r <= L) ring.fill(pd, r % 5, (H >> (2 * (6 - r))) & 1023u);
   }
   float E = CUDART_INF_F, x = CUDART_INF_F;
 
-  if constexpr (ScoreCfg<W>::PIPELINED)
-  {
-    // partial accumulators of the next row (t = 2..5); row 1 has no such predecessors
-    float Mp[Q], Ip[Q], xp = CUDART_INF_F;
+  // partial accumulators of the next row (t = 2..5); row 1 has no such predecessors
+  float Mp[Q], Ip[Q], xp = CUDART_INF_F;
 #pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      Mp[q] = CUDART_INF_F;
-      Ip[q] = CUDART_INF_F;
-    }
-#define DCP_ROWP(JJ_)                                                                            \
-  {                                                                                              \
-    if (l > L) break;                                                                            \
-    DCP_NEXT_NT()                                                                                \
-    dp_row_pipe<Q, JJ_>(s, Mp, Ip, xp, pd, H >> 10, (H >> 8) & 1023u, lane, NB, EB, JB, E, x);   \
-    ++l;                                                                                         \
-  }
-    int l = 1;
-    for (;;)
-    {
-      DCP_ROWP(1)
-      DCP_ROWP(2)
-      DCP_ROWP(3)
-      DCP_ROWP(4)
-      DCP_ROWP(0)
-    }
-#undef DCP_ROWP
-  }
-  else
+  for (int q = 0; q < Q; ++q)
   {
+    Mp[q] = CUDART_INF_F;
+    Ip[q] = CUDART_INF_F;
+  }
 #define DCP_ROW(JJ_)                                                                             \
   {                                                                                              \
     if (l > L) break;                                                                            \
     DCP_NEXT_NT()                                                                                \
-    dp_row<Q, W, JJ_>(s, pd, ring, H >> 10, H & 1023u, l + 5 <= L, phase, lane, warp, NB, EB, JB, mail, flags,  \
-                      l & 1, E, x);                                                              \
+    dp_row<Q, W, JJ_>(s, Mp, Ip, xp, pd, ring, (H >> 12) & 1023u, (H >> 10) & 1023u, H & 1023u, l + 1 <= L,  \
+                      l + 6 <= L, phase, lane, warp, NB, EB, JB, mail, flags, l & 1, E, x);      \
     ++l;                                                                                         \
   }
-    int l = 1;
-    for (;;)
-    {
-      DCP_ROW(1)
-      DCP_ROW(2)
-      DCP_ROW(3)
-      DCP_ROW(4)
-      DCP_ROW(0)
-    }
-#undef DCP_ROW
+  int l = 1;
+  for (;;)
+  {
+    DCP_ROW(1)
+    DCP_ROW(2)
+    DCP_ROW(3)
+    DCP_ROW(4)
+    DCP_ROW(0)
   }
+#undef DCP_ROW
 #undef DCP_NEXT_NT
 
   float const C = __shfl_sync(FULL_MASK, x, 2);
@@ -694,7 +587,6 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
   alt_cost = fminf(E + ET, C + CT); // viterbi.c:585-586, 599
   null_cost = R;                    // viterbi.c:718
 }
-
 
 template <int Q, int W>
 constexpr size_t score_smem_bytes()
