@@ -398,7 +398,10 @@ int launch_generic(dcpgpu_ctx *ctx, GenArgs a, int max_K)
   int const KG = (max_K + 31) & ~31;
   size_t const stride = (size_t)19 * KG;
   unsigned long long const want = (a.s.nitems + GEN_WARPS - 1) / GEN_WARPS;
-  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)4 * ctx->sm_count);
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel<TRACE>, GEN_THREADS, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
   size_t const need = stride * GEN_WARPS * grid;
   int rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, need);
   if (rc) return rc;

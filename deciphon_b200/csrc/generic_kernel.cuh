@@ -125,7 +125,7 @@ __device__ inline int trellis_walk(int K, int L, uint32_t const *xnodes, uint16_
 }
 
 template <bool TRACE>
-__global__ void __launch_bounds__(GEN_THREADS) generic_kernel(GenArgs a)
+__global__ void __launch_bounds__(GEN_THREADS, 5) generic_kernel(GenArgs a)
 {
   // special-state ring: xs[slot][0..6] = S, N, B, J, E, C, R
   __shared__ float xs_all[GEN_WARPS][6][8];
@@ -263,8 +263,7 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_kernel(GenArgs a)
         }
         float M = INF, I = INF;
         int mp = 0, ip = 0;
-        for (int t = T; t >= 1; --t)
-        {
+        auto candidates = [&](int t) {
           size_t const z = (size_t)((l - t) % 6) * KG;
           float const e = valid ? __ldg(pd.em + (size_t)code[t] * Kpad + pk) : INF;
           float const b = __ldg(&pd.nulbg[code[t]]).y;
@@ -278,7 +277,16 @@ __global__ void __launch_bounds__(GEN_THREADS) generic_kernel(GenArgs a)
           DCP_UPD(M, (pdv + dm) + e, mp, 15 + t - 1);
           DCP_UPD(I, (rI[z + k] + ii) + b, ip, 5 + t - 1); // II before MI, viterbi.c:535-536
           DCP_UPD(I, (rM[z + k] + mi) + b, ip, 0 + t - 1);
+        };
+        if (l >= 5)
+        { // steady state: all five emission lengths, unrolled so that the loads overlap
+#pragma unroll
+          for (int t = 5; t >= 1; --t)
+            candidates(t);
         }
+        else
+          for (int t = T; t >= 1; --t)
+            candidates(t);
         // delete chain inside the chunk, carried across chunks (viterbi.c:538,561-580)
         float mprev = __shfl_up_sync(FULL_MASK, M, 1);
         if (lane == 0) mprev = carryM;
