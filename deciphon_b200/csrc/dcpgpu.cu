@@ -392,22 +392,54 @@ int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
   }
 }
 
+// floats of scratch a generic-kernel launch over `nitems` pairs needs, and its grid
 template <bool TRACE>
-int launch_generic(dcpgpu_ctx *ctx, GenArgs a, int max_K)
+int generic_plan(dcpgpu_ctx *ctx, unsigned long long nitems, int max_K, unsigned *grid, size_t *floats)
 {
   int const KG = (max_K + 31) & ~31;
-  size_t const stride = (size_t)19 * KG;
-  unsigned long long const want = (a.s.nitems + GEN_WARPS - 1) / GEN_WARPS;
   int per_sm = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, generic_kernel<TRACE>, GEN_THREADS, 0));
   if (per_sm < 1) per_sm = 1;
-  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  size_t const need = stride * GEN_WARPS * grid;
-  int rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, need);
+  unsigned long long const want = (nitems + GEN_WARPS - 1) / GEN_WARPS;
+  *grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
+  *floats = (size_t)19 * KG * GEN_WARPS * *grid;
+  return 0;
+}
+
+template <bool TRACE>
+int launch_generic(dcpgpu_ctx *ctx, GenArgs a, int max_K)
+{
+  unsigned grid = 0;
+  size_t need = 0;
+  int rc = generic_plan<TRACE>(ctx, a.s.nitems, max_K, &grid, &need);
   if (rc) return rc;
+  if ((rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, need))) return rc;
   a.scratch = ctx->d_scratch;
-  a.scratch_stride = stride;
+  a.scratch_stride = (size_t)19 * ((max_K + 31) & ~31);
   generic_kernel<TRACE><<<grid, GEN_THREADS, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+template <int NW>
+int trace_cta_plan(dcpgpu_ctx *ctx, unsigned long long nitems, int max_K, unsigned *grid, size_t *floats)
+{
+  int const KG = (max_K + 31) & ~31;
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_cta_kernel<NW>, 32 * NW, 0));
+  if (per_sm < 1) per_sm = 1;
+  *grid = (unsigned)std::min<unsigned long long>(nitems, (unsigned long long)per_sm * ctx->sm_count);
+  *floats = (size_t)19 * KG * *grid;
+  return 0;
+}
+
+template <int NW>
+int launch_trace_cta(dcpgpu_ctx *ctx, GenArgs a, int max_K, unsigned grid, float *scratch)
+{
+  a.scratch = scratch;
+  a.scratch_stride = (size_t)19 * ((max_K + 31) & ~31);
+  trace_cta_kernel<NW><<<grid, 32 * NW, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return 0;
@@ -1040,24 +1072,73 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters + 26, 0, 2 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + 26, 0, 6 * sizeof(unsigned long long), ctx->stream));
 
-  GenArgs g{};
-  g.s.profiles = ctx->d_profiles;
-  g.s.reads = reads_view(ctx);
-  g.s.xt = ctx->d_xt[flags & 3u];
-  g.s.pairs = ctx->d_tpairs;
-  g.s.order = nullptr;
-  g.s.nitems = n;
-  g.s.counter = ctx->d_counters + 26;
-  g.s.out = ctx->d_tout;
-  g.s.nhits = ctx->d_counters + 27;
-  g.xnodes = ctx->d_xnodes;
-  g.nodes = ctx->d_nodes;
-  g.xnode_off = ctx->d_xnode_off;
-  g.node_off = ctx->d_node_off;
-  g.nsteps = ctx->d_nsteps;
-  if ((rc = launch_generic<true>(ctx, g, maxK))) return rc;
+  // Classes by profile size: one warp per pair up to K = 256 (throughput), a CTA of 2/4/8 warps
+  // per pair above (the pass would otherwise last as long as its largest profile).
+  std::vector<long long> tb[4];
+  int tmaxK[4] = {1, 1, 1, 1};
+  for (int64_t i = 0; i < npairs; ++i)
+  {
+    int const K = ctx->h_profiles[(size_t)pairs[i].profile].K;
+    int const c = K <= 256 ? 0 : K <= 512 ? 1 : K <= 1024 ? 2 : 3;
+    tb[c].push_back(i);
+    tmaxK[c] = std::max(tmaxK[c], K);
+  }
+  std::vector<long long> torder;
+  size_t tfirst[5];
+  for (int c = 0; c < 4; ++c)
+  {
+    tfirst[c] = torder.size();
+    torder.insert(torder.end(), tb[c].begin(), tb[c].end());
+  }
+  tfirst[4] = torder.size();
+  if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, n))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_order, torder.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+
+  unsigned tgrid[4] = {0, 0, 0, 0};
+  size_t tfloats[4] = {0, 0, 0, 0};
+  if (!tb[0].empty() && (rc = generic_plan<true>(ctx, tb[0].size(), tmaxK[0], &tgrid[0], &tfloats[0]))) return rc;
+  if (!tb[1].empty() && (rc = trace_cta_plan<2>(ctx, tb[1].size(), tmaxK[1], &tgrid[1], &tfloats[1]))) return rc;
+  if (!tb[2].empty() && (rc = trace_cta_plan<4>(ctx, tb[2].size(), tmaxK[2], &tgrid[2], &tfloats[2]))) return rc;
+  if (!tb[3].empty() && (rc = trace_cta_plan<8>(ctx, tb[3].size(), tmaxK[3], &tgrid[3], &tfloats[3]))) return rc;
+  if ((rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, tfloats[0] + tfloats[1] + tfloats[2] + tfloats[3]))) return rc;
+
+  // largest profiles first: they bound the duration of the pass
+  size_t sc_off = 0;
+  static int const cursor_slot[4] = {26, 29, 30, 31};
+  for (int c = 3; c >= 0; --c)
+  {
+    if (tb[c].empty()) continue;
+    GenArgs g{};
+    g.s.profiles = ctx->d_profiles;
+    g.s.reads = reads_view(ctx);
+    g.s.xt = ctx->d_xt[flags & 3u];
+    g.s.pairs = ctx->d_tpairs;
+    g.s.order = ctx->d_order + tfirst[c];
+    g.s.nitems = tb[c].size();
+    g.s.counter = ctx->d_counters + cursor_slot[c];
+    g.s.out = ctx->d_tout;
+    g.s.nhits = ctx->d_counters + 27;
+    g.xnodes = ctx->d_xnodes;
+    g.nodes = ctx->d_nodes;
+    g.xnode_off = ctx->d_xnode_off;
+    g.node_off = ctx->d_node_off;
+    g.nsteps = ctx->d_nsteps;
+    float *scr = ctx->d_scratch + sc_off;
+    sc_off += tfloats[c];
+    if (c == 0)
+    {
+      g.scratch = scr;
+      g.scratch_stride = (size_t)19 * ((tmaxK[0] + 31) & ~31);
+      generic_kernel<true><<<tgrid[0], GEN_THREADS, 0, ctx->stream>>>(g);
+      CU(cudaGetLastError());
+      ctx->launches += 1;
+    }
+    else if (c == 1) { if ((rc = launch_trace_cta<2>(ctx, g, tmaxK[1], tgrid[1], scr))) return rc; }
+    else if (c == 2) { if ((rc = launch_trace_cta<4>(ctx, g, tmaxK[2], tgrid[2], scr))) return rc; }
+    else { if ((rc = launch_trace_cta<8>(ctx, g, tmaxK[3], tgrid[3], scr))) return rc; }
+  }
 
   std::vector<float2> h(n);
   CU(cudaMemcpyAsync(h.data(), ctx->d_tout, n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));

@@ -361,6 +361,226 @@ __global__ void __launch_bounds__(GEN_THREADS, 5) generic_kernel(GenArgs a)
   }
 }
 
+// ---- trace pass for large profiles: one CTA of NW warps per pair -----------------------------
+// generic_kernel<true> walks the K/32 node chunks of a row serially in one warp, so the pass
+// lasts as long as its largest profile (measured: the trace launch equals the time of the one
+// K ~ 1600 hit in it).  Here the chunks of a row are spread over the NW warps of a CTA for the
+// M/I candidates (phase 1, no dependency between chunks), then warp 0 alone resolves the delete
+// chain, E, the special states and the trellis xnode of the row (phase 2, serial in k).  Same
+// arithmetic, candidate order and strict-less updates as generic_kernel.
+template <int NW>
+__global__ void __launch_bounds__(32 * NW) trace_cta_kernel(GenArgs a)
+{
+  __shared__ float xs[6][8]; // special-state ring: S, N, B, J, E, C, R
+  __shared__ unsigned long long next_item;
+  int const lane = threadIdx.x & 31;
+  int const warp = threadIdx.x >> 5;
+  float *scratch = a.scratch + (size_t)blockIdx.x * a.scratch_stride;
+  float const INF = CUDART_INF_F;
+
+  for (;;)
+  {
+    if (threadIdx.x == 0) next_item = atomicAdd(a.s.counter, 1ULL);
+    __syncthreads();
+    unsigned long long const item = next_item;
+    __syncthreads();
+    if (item >= a.s.nitems) break;
+    long long const oidx = a.s.order ? a.s.order[item] : (long long)item;
+    Pair const pr = a.s.pairs[oidx];
+    int const L = pr.len;
+    ProfileDesc const pd = a.s.profiles[pr.profile];
+    int const K = pd.K, Kpad = pd.Kpad;
+    int const KG = (K + 31) & ~31;
+    float *rM = scratch, *rI = scratch + 6 * (size_t)KG, *rD = scratch + 12 * (size_t)KG;
+    int *posk = reinterpret_cast<int *>(scratch + 18 * (size_t)KG);
+    float const *xt = a.s.xt + (size_t)L * X_STRIDE;
+    float const RR = xt[X_RR], SN = xt[X_SN], NN = xt[X_NN], SB = xt[X_SB], NB = xt[X_NB],
+                EB = xt[X_EB], JB = xt[X_JB], EJ = xt[X_EJ], JJ = xt[X_JJ], EC = xt[X_EC],
+                CC = xt[X_CC], ET = xt[X_ET], CT = xt[X_CT];
+    uint32_t *xnodes = a.xnodes + a.xnode_off[oidx];
+    uint16_t *nodes = a.nodes + a.node_off[oidx];
+
+    // row 0 (viterbi.c:472-474; before() writes all-zero trellis fields, :602-629)
+    for (int k = threadIdx.x; k < KG; k += 32 * NW)
+    {
+      posk[k] = k < K ? layout_pos(k, pd.Q, 32 * pd.W) : 0;
+      for (int sl = 0; sl < 6; ++sl)
+      {
+        rM[sl * (size_t)KG + k] = INF;
+        rI[sl * (size_t)KG + k] = INF;
+        rD[sl * (size_t)KG + k] = INF;
+      }
+      if (k < K) nodes[k] = 0;
+    }
+    if (threadIdx.x < 48) xs[threadIdx.x >> 3][threadIdx.x & 7] = INF;
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+      xs[0][0] = 0.0f; // S
+      xs[0][2] = SB;   // B
+      xs[0][6] = -RR;  // R(0), viterbi.c:703
+      xnodes[0] = 0;
+    }
+    __syncthreads();
+
+    uint32_t const *wp = a.s.reads.words + a.s.reads.seq_word[pr.seq] + (pr.start >> 4);
+    uint32_t word = __ldg(wp) >> (2 * (pr.start & 15));
+    int left = 16 - (pr.start & 15);
+    unsigned hist = 0;
+    float Tv = INF, Rv = INF;
+
+    for (int l = 1; l <= L; ++l)
+    {
+      hist = ((hist << 2) | (word & 3u)) & 1023u;
+      word >>= 2;
+      if (--left == 0) { word = __ldg(++wp); left = 16; }
+      int const sl = l % 6;
+      int const T = l < 5 ? l : 5;
+      int code[6];
+      code[1] = hist & 3;
+      code[2] = 4 + (hist & 15);
+      code[3] = 20 + (hist & 63);
+      code[4] = 84 + (hist & 255);
+      code[5] = 340 + (hist & 1023);
+
+      // ---- phase 1: M and I of every chunk, chunks spread over the warps ----
+      for (int c0 = 32 * warp; c0 < KG; c0 += 32 * NW)
+      {
+        int const k = c0 + lane;
+        bool const valid = k < K;
+        int const pk = posk[k];
+        float bm = INF, mm = INF, mi = INF, im = INF, ii = INF, dm = INF;
+        if (valid)
+        {
+          bm = __ldg(pd.core + C_BM * Kpad + pk);
+          mm = __ldg(pd.core + C_MM * Kpad + pk);
+          mi = __ldg(pd.core + C_MI * Kpad + pk);
+          im = __ldg(pd.core + C_IM * Kpad + pk);
+          ii = __ldg(pd.core + C_II * Kpad + pk);
+          dm = __ldg(pd.core + C_DM * Kpad + pk);
+        }
+        float M = INF, I = INF;
+        int mp = 0, ip = 0;
+        auto candidates = [&](int t) {
+          size_t const z = (size_t)((l - t) % 6) * KG;
+          float const e = valid ? __ldg(pd.em + (size_t)code[t] * Kpad + pk) : INF;
+          float const b = __ldg(&pd.nulbg[code[t]]).y;
+          float const Bz = xs[(l - t) % 6][2];
+          float const pm = k > 0 ? rM[z + k - 1] : INF;
+          float const pi = k > 0 ? rI[z + k - 1] : INF;
+          float const pdv = k > 0 ? rD[z + k - 1] : INF;
+          DCP_UPD(M, (Bz + bm) + e, mp, 0 + t - 1);
+          DCP_UPD(M, (pm + mm) + e, mp, 5 + t - 1);
+          DCP_UPD(M, (pi + im) + e, mp, 10 + t - 1);
+          DCP_UPD(M, (pdv + dm) + e, mp, 15 + t - 1);
+          DCP_UPD(I, (rI[z + k] + ii) + b, ip, 5 + t - 1); // II before MI, viterbi.c:535-536
+          DCP_UPD(I, (rM[z + k] + mi) + b, ip, 0 + t - 1);
+        };
+        if (l >= 5)
+        {
+#pragma unroll
+          for (int t = 5; t >= 1; --t)
+            candidates(t);
+        }
+        else
+          for (int t = T; t >= 1; --t)
+            candidates(t);
+        rM[(size_t)sl * KG + k] = M;
+        rI[(size_t)sl * KG + k] = I;
+        if (valid) nodes[(size_t)l * K + k] = (uint16_t)((unsigned)mp | ((unsigned)ip << 6));
+      }
+      __syncthreads();
+
+      // ---- phase 2 (warp 0): special states, delete chain, E, B, T, trellis xnode ----
+      if (warp == 0)
+      {
+        float N = INF, Jv = INF, C = INF, R = INF;
+        int pN = 0, pJ = 0, pC = 0;
+        for (int t = T; t >= 1; --t)
+        {
+          int const z = (l - t) % 6;
+          float const nil = __ldg(&pd.nulbg[code[t]]).x;
+          DCP_UPD(N, xs[z][0] + SN + nil, pN, 0 + t - 1);
+          DCP_UPD(N, xs[z][1] + NN + nil, pN, 5 + t - 1);
+          DCP_UPD(Jv, xs[z][4] + EJ + nil, pJ, 0 + t - 1);
+          DCP_UPD(Jv, xs[z][3] + JJ + nil, pJ, 5 + t - 1);
+          DCP_UPD(C, xs[z][4] + EC + nil, pC, 0 + t - 1);
+          DCP_UPD(C, xs[z][5] + CC + nil, pC, 5 + t - 1);
+          R = fminf(R, xs[z][6] + RR + nil);
+        }
+        float carryM = INF, carryD = INF;
+        float ev = INF;
+        int ei = 0;
+        for (int c0 = 0; c0 < KG; c0 += 32)
+        {
+          int const k = c0 + lane;
+          bool const valid = k < K;
+          int const pk = posk[k];
+          float const md = valid ? __ldg(pd.core + C_MD * Kpad + pk) : INF;
+          float const dd = valid ? __ldg(pd.core + C_DD * Kpad + pk) : INF;
+          float const M = rM[(size_t)sl * KG + k];
+          float mprev = __shfl_up_sync(FULL_MASK, M, 1);
+          if (lane == 0) mprev = carryM;
+          float D = mprev + md;
+          int dbit = 0;
+          for (;;)
+          {
+            float dp = __shfl_up_sync(FULL_MASK, D, 1);
+            if (lane == 0) dp = carryD;
+            float const c = dp + dd;
+            bool const imp = c < D;
+            if (!__any_sync(FULL_MASK, imp)) break;
+            if (imp) { D = c; dbit = 1; }
+          }
+          carryM = __shfl_sync(FULL_MASK, M, 31);
+          carryD = __shfl_sync(FULL_MASK, D, 31);
+          DCP_UPD(ev, M, ei, 2 * k + 0);
+          DCP_UPD(ev, D, ei, 2 * k + 1);
+          rD[(size_t)sl * KG + k] = D;
+          if (valid && dbit) nodes[(size_t)l * K + k] |= (uint16_t)(1u << 5);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+          float const ov = __shfl_xor_sync(FULL_MASK, ev, o);
+          int const oi = __shfl_xor_sync(FULL_MASK, ei, o);
+          if (ov < ev || (ov == ev && oi < ei)) { ev = ov; ei = oi; }
+        }
+        float B = INF;
+        int pB = 0, pT = 0;
+        DCP_UPD(B, N + NB, pB, 1);
+        DCP_UPD(B, ev + EB, pB, 2);
+        DCP_UPD(B, Jv + JB, pB, 3);
+        Tv = INF;
+        DCP_UPD(Tv, ev + ET, pT, 0);
+        DCP_UPD(Tv, C + CT, pT, 1);
+        Rv = R;
+        if (lane == 0)
+        {
+          xs[sl][0] = INF;
+          xs[sl][1] = N;
+          xs[sl][2] = B;
+          xs[sl][3] = Jv;
+          xs[sl][4] = ev;
+          xs[sl][5] = C;
+          xs[sl][6] = R;
+          xnodes[l] = (uint32_t)pN | ((uint32_t)pB << 4) | ((uint32_t)ei << 6) | ((uint32_t)pC << 21) |
+                      ((uint32_t)pT << 25) | ((uint32_t)pJ << 26);
+        }
+      }
+      __syncthreads();
+    }
+
+    if (threadIdx.x == 0)
+    {
+      a.s.out[oidx] = make_float2(Rv, Tv);
+      __threadfence();
+      a.nsteps[oidx] = trellis_walk(K, L, xnodes, nodes, 0, nullptr, nullptr);
+    }
+    __syncthreads();
+  }
+}
+
 struct WalkArgs
 {
   ProfileDesc const *profiles;
