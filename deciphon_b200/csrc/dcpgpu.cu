@@ -9,6 +9,7 @@
 #include "generic_kernel.cuh"
 #include "layout.cuh"
 #include "score_kernel.cuh"
+#include "trace_argmin.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -114,6 +115,12 @@ struct dcpgpu_ctx
   size_t nsteps_cap = 0;
   float2 *d_tout = nullptr;
   size_t tout_cap = 0;
+  long long *d_hit_idx = nullptr;
+  size_t hit_idx_cap = 0;
+  float *d_dump = nullptr;
+  size_t dump_cap = 0;
+  long long *d_dump_off = nullptr, *d_tile_off = nullptr;
+  size_t dump_off_cap = 0, tile_off_cap = 0;
   uint16_t *d_step_ids = nullptr;
   size_t step_ids_cap = 0;
   uint8_t *d_step_sz = nullptr;
@@ -342,7 +349,7 @@ int kernel_class(dcpgpu_ctx const *ctx, int profile)
   return 0;
 }
 
-template <int Q, int W>
+template <int Q, int W, bool DUMP = false>
 int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
 {
   constexpr int T = ScoreCfg<W>::THREADS, G = ScoreCfg<W>::GROUPS;
@@ -350,47 +357,50 @@ int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
   static bool configured = false;
   if (!configured)
   {
-    CU(cudaFuncSetAttribute(score_reg_kernel<Q, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
+    CU(cudaFuncSetAttribute(score_reg_kernel<Q, W, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
     configured = true;
   }
   int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W>, T, SMEM));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W, DUMP>, T, SMEM));
   if (per_sm < 1) per_sm = 1;
   unsigned long long const want = (a.nitems + G - 1) / G;
   unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  score_reg_kernel<Q, W><<<grid, T, SMEM, ctx->stream>>>(a);
+  score_reg_kernel<Q, W, DUMP><<<grid, T, SMEM, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return 0;
 }
 
-int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
+template <bool DUMP>
+int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 {
   switch (cls)
   {
-  case 1: return launch_reg<1, 1>(ctx, a);
-  case 2: return launch_reg<2, 1>(ctx, a);
-  case 3: return launch_reg<3, 1>(ctx, a);
-  case 4: return launch_reg<4, 1>(ctx, a);
-  case 5: return launch_reg<5, 1>(ctx, a);
-  case 6: return launch_reg<6, 1>(ctx, a);
-  case 7: return launch_reg<7, 1>(ctx, a);
-  case 8: return launch_reg<8, 1>(ctx, a);
-  case 9: return launch_reg<5, 2>(ctx, a);
-  case 10: return launch_reg<6, 2>(ctx, a);
-  case 11: return launch_reg<7, 2>(ctx, a);
-  case 12: return launch_reg<8, 2>(ctx, a);
-  case 13: return launch_reg<5, 4>(ctx, a);
-  case 14: return launch_reg<6, 4>(ctx, a);
-  case 15: return launch_reg<7, 4>(ctx, a);
-  case 16: return launch_reg<8, 4>(ctx, a);
-  case 17: return launch_reg<5, 8>(ctx, a);
-  case 18: return launch_reg<6, 8>(ctx, a);
-  case 19: return launch_reg<7, 8>(ctx, a);
-  case 20: return launch_reg<8, 8>(ctx, a);
+  case 1: return launch_reg<1, 1, DUMP>(ctx, a);
+  case 2: return launch_reg<2, 1, DUMP>(ctx, a);
+  case 3: return launch_reg<3, 1, DUMP>(ctx, a);
+  case 4: return launch_reg<4, 1, DUMP>(ctx, a);
+  case 5: return launch_reg<5, 1, DUMP>(ctx, a);
+  case 6: return launch_reg<6, 1, DUMP>(ctx, a);
+  case 7: return launch_reg<7, 1, DUMP>(ctx, a);
+  case 8: return launch_reg<8, 1, DUMP>(ctx, a);
+  case 9: return launch_reg<5, 2, DUMP>(ctx, a);
+  case 10: return launch_reg<6, 2, DUMP>(ctx, a);
+  case 11: return launch_reg<7, 2, DUMP>(ctx, a);
+  case 12: return launch_reg<8, 2, DUMP>(ctx, a);
+  case 13: return launch_reg<5, 4, DUMP>(ctx, a);
+  case 14: return launch_reg<6, 4, DUMP>(ctx, a);
+  case 15: return launch_reg<7, 4, DUMP>(ctx, a);
+  case 16: return launch_reg<8, 4, DUMP>(ctx, a);
+  case 17: return launch_reg<5, 8, DUMP>(ctx, a);
+  case 18: return launch_reg<6, 8, DUMP>(ctx, a);
+  case 19: return launch_reg<7, 8, DUMP>(ctx, a);
+  case 20: return launch_reg<8, 8, DUMP>(ctx, a);
   default: return fail(ctx, DCPGPU_EINVAL, "bad kernel class");
   }
 }
+
+int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a) { return launch_class_t<false>(ctx, cls, a); }
 
 // floats of scratch a generic-kernel launch over `nitems` pairs needs, and its grid
 template <bool TRACE>
@@ -588,6 +598,10 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_nsteps);
   cudaFree(ctx->d_tout);
   cudaFree(ctx->d_step_ids);
+  cudaFree(ctx->d_dump);
+  cudaFree(ctx->d_hit_idx);
+  cudaFree(ctx->d_dump_off);
+  cudaFree(ctx->d_tile_off);
   cudaFree(ctx->d_step_sz);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -1003,8 +1017,9 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
   CU(cudaStreamSynchronize(ctx->stream));
   *nhits = (int64_t)n;
   if (!hit_index || cap == 0 || n == 0) return 0;
-  long long *d_idx = nullptr;
-  CU(cudaMalloc(reinterpret_cast<void **>(&d_idx), (size_t)n * sizeof(long long)));
+  int rc_e = ensure(ctx, ctx->d_hit_idx, ctx->hit_idx_cap, (size_t)n);
+  if (rc_e) return rc_e;
+  long long *d_idx = ctx->d_hit_idx;
   CU(cudaMemsetAsync(ctx->d_counters + 25, 0, sizeof(unsigned long long), ctx->stream));
   long long const N = ctx->last_n;
   hits_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, N, ctx->d_counters + 25,
@@ -1013,7 +1028,6 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
   std::vector<long long> h((size_t)n);
   cudaError_t e = cudaMemcpyAsync(h.data(), d_idx, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_idx);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "hits_fetch");
   std::sort(h.begin(), h.end());
   for (int64_t i = 0; i < std::min<int64_t>(cap, (int64_t)n); ++i)
@@ -1074,11 +1088,132 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_counters + 26, 0, 6 * sizeof(unsigned long long), ctx->stream));
 
+  // ---- fast route: pairs whose profile runs on a register kernel -------------------------------
+  // value dump by score_reg_kernel<Q,W,DUMP> + parallel argmin kernel (trace_argmin.cuh), in chunks
+  // bounded by the dump size (12 bytes per DP cell).
+  std::vector<long long> fast, slow;
+  for (int64_t i = 0; i < npairs; ++i)
+    (kernel_class(ctx, pairs[i].profile) != 0 ? fast : slow).push_back(i);
+  if (!fast.empty())
+  {
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    size_t const have = ctx->dump_cap * sizeof(float);
+    size_t const budget = std::min<size_t>((fr + have) / 2, size_t(24) << 30) / sizeof(float);
+    if ((rc = ensure(ctx, ctx->d_dump_off, ctx->dump_off_cap, n))) return rc;
+    std::vector<long long> dump_off(n, 0);
+    // class-major: every launch then holds many pairs of ONE kernel class (full occupancy)
+    std::vector<std::vector<long long>> by_class(NCLASS);
+    for (long long i : fast) by_class[(size_t)kernel_class(ctx, pairs[i].profile)].push_back(i);
+    // size the dump buffer ONCE (largest chunk any class will need): reallocating tens of GB
+    // between launches costs more than the kernels
+    {
+      size_t need = 0;
+      for (int cls = 1; cls < NCLASS; ++cls)
+      {
+        size_t tot_cls = 0;
+        for (long long i : by_class[(size_t)cls])
+          tot_cls += DumpView::floats(pairs[i].len, ctx->h_profiles[(size_t)pairs[i].profile].Kpad);
+        need = std::max(need, std::min(tot_cls, budget));
+        for (long long i : by_class[(size_t)cls])
+          need = std::max(need, DumpView::floats(pairs[i].len, ctx->h_profiles[(size_t)pairs[i].profile].Kpad));
+      }
+      if (need > ctx->dump_cap)
+      {
+        if (ctx->d_dump) CU(cudaFree(ctx->d_dump));
+        ctx->d_dump = nullptr;
+        ctx->dump_cap = 0;
+        CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_dump), need * sizeof(float)));
+        ctx->dump_cap = need;
+      }
+    }
+    for (int cls = NCLASS - 1; cls >= 1; --cls)
+    {
+      std::vector<long long> const &list = by_class[(size_t)cls];
+      size_t c0 = 0;
+      while (c0 < list.size())
+      {
+        // chunk [c0, c1) bounded by the dump budget
+        size_t c1 = c0, floats = 0;
+        while (c1 < list.size())
+        {
+          dcpgpu_pair const &pr = pairs[list[c1]];
+          size_t const f = DumpView::floats(pr.len, ctx->h_profiles[(size_t)pr.profile].Kpad);
+          if (c1 > c0 && floats + f > budget) break;
+          dump_off[(size_t)list[c1]] = (long long)floats;
+          floats += f;
+          ++c1;
+        }
+        size_t const cn = c1 - c0;
+        if (floats > ctx->dump_cap) return fail(ctx, DCPGPU_ESTATE, "trace: dump buffer too small (internal error)");
+        std::vector<long long> tile_off(cn + 1, 0), doff(cn);
+        for (size_t i = 0; i < cn; ++i)
+        {
+          tile_off[i + 1] = tile_off[i] + (pairs[list[c0 + i]].len + ARGMIN_ROWS - 1) / ARGMIN_ROWS;
+          doff[i] = dump_off[(size_t)list[c0 + i]];
+        }
+        if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, cn))) return rc;
+        if ((rc = ensure(ctx, ctx->d_tile_off, ctx->tile_off_cap, cn + 1))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_order, list.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (cn + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        // dump offsets are indexed by the item's position in this launch
+        CU(cudaMemcpyAsync(ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_counters + cls, 0, sizeof(unsigned long long), ctx->stream));
+        ScoreArgs sa{};
+        sa.profiles = ctx->d_profiles;
+        sa.reads = reads_view(ctx);
+        sa.xt = ctx->d_xt[flags & 3u];
+        sa.pairs = ctx->d_tpairs;
+        sa.order = ctx->d_order;
+        sa.nitems = cn;
+        sa.counter = ctx->d_counters + cls;
+        sa.out = ctx->d_tout;
+        sa.nhits = ctx->d_counters + 27;
+        sa.dump = ctx->d_dump;
+        sa.dump_off = ctx->d_dump_off;
+        if ((rc = launch_class_t<true>(ctx, cls, sa))) return rc;
+        ArgminArgs g{};
+        g.profiles = ctx->d_profiles;
+        g.reads = reads_view(ctx);
+        g.xt = ctx->d_xt[flags & 3u];
+        g.pairs = ctx->d_tpairs;
+        g.order = ctx->d_order;
+        g.tile_off = ctx->d_tile_off;
+        g.nitems = (long long)cn;
+        g.dump = ctx->d_dump;
+        g.dump_off = ctx->d_dump_off;
+        g.xnodes = ctx->d_xnodes;
+        g.nodes = ctx->d_nodes;
+        g.xnode_off = ctx->d_xnode_off;
+        g.node_off = ctx->d_node_off;
+        trace_argmin_kernel<<<(unsigned)tile_off[cn], ARGMIN_THREADS, 0, ctx->stream>>>(g);
+        CU(cudaGetLastError());
+        WalkCountArgs w{};
+        w.profiles = ctx->d_profiles;
+        w.pairs = ctx->d_tpairs;
+        w.order = ctx->d_order;
+        w.nitems = (long long)cn;
+        w.xnodes = ctx->d_xnodes;
+        w.nodes = ctx->d_nodes;
+        w.xnode_off = ctx->d_xnode_off;
+        w.node_off = ctx->d_node_off;
+        w.nsteps = ctx->d_nsteps;
+        walk_count_kernel<<<(unsigned)((cn + 63) / 64), 64, 0, ctx->stream>>>(w);
+        CU(cudaGetLastError());
+        ctx->launches += 2;
+        // host vectors and the device order/tile buffers are reused by the next chunk
+        CU(cudaStreamSynchronize(ctx->stream));
+        c0 = c1;
+      }
+    }
+  }
+
+  // ---- slow route (profiles the register kernels cannot run: K > 2048 or a negative cost) ----
   // Classes by profile size: one warp per pair up to K = 256 (throughput), a CTA of 2/4/8 warps
   // per pair above (the pass would otherwise last as long as its largest profile).
   std::vector<long long> tb[4];
   int tmaxK[4] = {1, 1, 1, 1};
-  for (int64_t i = 0; i < npairs; ++i)
+  for (long long i : slow)
   {
     int const K = ctx->h_profiles[(size_t)pairs[i].profile].K;
     int const c = K <= 256 ? 0 : K <= 512 ? 1 : K <= 1024 ? 2 : 3;
@@ -1093,8 +1228,11 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     torder.insert(torder.end(), tb[c].begin(), tb[c].end());
   }
   tfirst[4] = torder.size();
-  if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, n))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_order, torder.data(), n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  if (!torder.empty())
+  {
+    if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, torder.size()))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_order, torder.data(), torder.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  }
 
   unsigned tgrid[4] = {0, 0, 0, 0};
   size_t tfloats[4] = {0, 0, 0, 0};

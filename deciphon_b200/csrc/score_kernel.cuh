@@ -66,6 +66,25 @@ struct ScoreArgs
   unsigned long long *counter; // work-stealing cursor
   float2 *out;                 // {null cost, alt cost} per pair
   unsigned long long *nhits;
+  // DUMP variant (trace pass): every row's M, I, D and special-state values go to global memory
+  float *dump;                 // pool
+  long long const *dump_off;   // per item of this launch: floats offset of its block (see DumpView)
+};
+
+// Layout of one traced pair's value dump: rows l = 1..L (row 0 is all +INF except B = SB).
+//   M, I, D : [L][Kpad] each, node k at column k (= vl*Q + q)
+//   xs      : [L][8] = N, B, J, E, C
+struct DumpView
+{
+  float *M, *I, *D, *xs;
+  __host__ __device__ static size_t floats(int L, int Kpad) { return (size_t)L * (3 * (size_t)Kpad + 8); }
+  __host__ __device__ DumpView(float *base, int L, int Kpad)
+  {
+    M = base;
+    I = M + (size_t)L * Kpad;
+    D = I + (size_t)L * Kpad;
+    xs = D + (size_t)L * Kpad;
+  }
 };
 
 struct __align__(16) Mail
@@ -206,6 +225,18 @@ __device__ __forceinline__ void load_chunks_smem(float (&e)[Q], float const *row
 }
 
 // The TMA ring of one pair: 5 stages (ring slot J) x 2 rows (4-mer, 5-mer) x ROW floats.
+// What the row code sees of the dump: nothing at all unless DUMP.
+template <bool DUMP>
+struct DumpRef
+{
+  __device__ __forceinline__ DumpRef(float *, int, int) {}
+};
+template <>
+struct DumpRef<true> : DumpView
+{
+  __device__ __forceinline__ DumpRef(float *base, int L, int Kpad) : DumpView(base, L, Kpad) {}
+};
+
 template <int Q, int W>
 struct Ring
 {
@@ -299,12 +330,12 @@ __device__ __forceinline__ float e_partial(float const (&M)[Q], float const (&D)
 // partial accumulators Mp/Ip/xp it inherits before its own delete chain starts.
 //   hist  = the five nucleotides ending at l-1 (codes of row l), hist1 = ending at l (row l+1),
 //   hist6 = ending at l+5 (row l+6: its long-code rows are requested from the TMA ring now).
-template <int Q, int W, int J>
+template <int Q, int W, int J, bool DUMP>
 __device__ __forceinline__ void dp_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q], float &xp, ProfileDesc const &pd,
                                        Ring<Q, W> const &ring, unsigned hist, unsigned hist1, unsigned hist6,
                                        bool have_next, bool refill, unsigned &phase, int lane, int warp, float NB,
                                        float EB, float JB, Mail *mail, int volatile *flags, int par, float &E,
-                                       float &x)
+                                       float &x, DumpRef<DUMP> const &dv, int l)
 {
   constexpr int VL = 32 * W;
   constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
@@ -471,6 +502,30 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q
   float const B = min3(N + NB, E + EB, Jv + JB); // viterbi.c:495-496,582-583
   s.px[J] = fminf(E + s.xa, x + s.xb);
 
+  if constexpr (DUMP)
+  { // trace pass: the row's final values, for the argmin kernels
+    size_t const at = (size_t)(l - 1) * pd.Kpad + (size_t)vl * Q;
+#pragma unroll
+    for (int q = 0; q < Q; ++q)
+    {
+      dv.M[at + q] = M[q];
+      dv.I[at + q] = I[q];
+      dv.D[at + q] = D[q];
+    }
+    if (warp == 0)
+    {
+      float *xr = dv.xs + (size_t)(l - 1) * 8;
+      if (lane == 0)
+      {
+        xr[0] = N;
+        xr[1] = B;
+        xr[2] = Jv;
+        xr[3] = E;
+      }
+      if (lane == 2) xr[4] = x; // C(l)
+    }
+  }
+
   // P(l), Q(l) into the slot that held row l-5
   s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
 #pragma unroll
@@ -481,11 +536,12 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q
     s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
 }
 
-template <int Q, int W>
+template <int Q, int W, bool DUMP>
 __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> const &ring, unsigned &phase,
                                           uint32_t const *__restrict__ words, int start, int L,
                                           float const *__restrict__ xt, int lane, int warp, Mail *mail,
-                                          int volatile *flags, float &null_cost, float &alt_cost)
+                                          int volatile *flags, float &null_cost, float &alt_cost,
+                                          DumpRef<DUMP> const &dv)
 {
   constexpr int VL = 32 * W;
   Lane<Q> s;
@@ -566,8 +622,9 @@ __device__ __forceinline__ void score_one(ProfileDesc const &pd, Ring<Q, W> cons
   {                                                                                              \
     if (l > L) break;                                                                            \
     DCP_NEXT_NT()                                                                                \
-    dp_row<Q, W, JJ_>(s, Mp, Ip, xp, pd, ring, (H >> 12) & 1023u, (H >> 10) & 1023u, H & 1023u, l + 1 <= L,  \
-                      l + 6 <= L, phase, lane, warp, NB, EB, JB, mail, flags, l & 1, E, x);      \
+    dp_row<Q, W, JJ_, DUMP>(s, Mp, Ip, xp, pd, ring, (H >> 12) & 1023u, (H >> 10) & 1023u, H & 1023u,      \
+                            l + 1 <= L, l + 6 <= L, phase, lane, warp, NB, EB, JB, mail, flags, l & 1, E, x,  \
+                            dv, l);                                                              \
     ++l;                                                                                         \
   }
   int l = 1;
@@ -594,7 +651,7 @@ constexpr size_t score_smem_bytes()
   return ScoreCfg<W>::TMA_RING ? (size_t)ScoreCfg<W>::GROUPS * (5 * 2 * Ring<Q, W>::ROW * sizeof(float) + 64) : 256;
 }
 
-template <int Q, int W>
+template <int Q, int W, bool DUMP = false>
 __global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreArgs a)
 {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -671,8 +728,9 @@ __global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreAr
       len = min(w, a.reads.seq_len[sq]);
     }
     float nul, alt;
-    score_one<Q, W>(pd, ring, phase, a.reads.words + a.reads.seq_word[sq], start, len,
-                    a.xt + (size_t)len * X_STRIDE, lane, warp, mail, flags, nul, alt);
+    DumpRef<DUMP> const dv(DUMP ? a.dump + a.dump_off[item] : nullptr, len, pd.Kpad);
+    score_one<Q, W, DUMP>(pd, ring, phase, a.reads.words + a.reads.seq_word[sq], start, len,
+                          a.xt + (size_t)len * X_STRIDE, lane, warp, mail, flags, nul, alt, dv);
     if (lane == 0 && warp == 0)
     {
       a.out[oidx] = make_float2(nul, alt);
