@@ -137,19 +137,19 @@ def test_scan_reproduces_golden_snap(tmp_path, golden_profiles, golden_reads):
 
 
 @pytest.mark.gpu
-def test_scan_windows_long_read(tmp_path, node_pool, oracle):
+@pytest.mark.parametrize("K,copies", [(20, 8), (3, 12)])  # K = 3: the shape of c-core/massive.hmm (config 2)
+def test_scan_windows_long_read(tmp_path, node_pool, oracle, K, copies):
     """A read longer than min(50K, 100000) is cut into overlapping window.c windows whose starts
     depend on the previous window's hit; rows must match an oracle-driven scan of the same read."""
     from deciphon_b200 import synth
     from deciphon_b200.dcp_file import write_dcp
     from deciphon_b200.scan import Batch, Scan, Sequence
     rng = np.random.default_rng(77)
-    K = 20
-    prof = synth.synth_profile(rng, K, node_pool, name="SYN20")
+    prof = synth.synth_profile(rng, K, node_pool, name="SYN%d" % K)
     cons = np.argmax(prof.emission[:K, 20:84], axis=1)
     cons = np.stack([cons // 16, (cons // 4) % 4, cons % 4], axis=1).reshape(-1).astype(np.uint8)
     parts = []
-    for i in range(8):
+    for i in range(copies):
         parts += [synth.random_read(rng, int(rng.integers(150, 500))), synth.mutate(rng, cons, 0.03)]
     x = np.concatenate(parts + [synth.random_read(rng, 333)])
     data = "".join("ACGT"[v] for v in x)
@@ -181,7 +181,60 @@ def test_scan_windows_long_read(tmp_path, node_pool, oracle):
             w = g.send(last)
     except StopIteration:
         pass
-    assert len(want) >= 3 and len(got) == len(want)
+    assert (len(want) >= 3 or K < 10) and len(got) == len(want)
     for row, (idx, a, b, hs, he, lrt, names) in zip(got, want):
         assert (int(row[1]), int(row[2]), int(row[3]), int(row[5]), int(row[6]), row[9]) == (idx, a, b, hs, he, lrt)
         assert [m.split(",")[1] for m in row[11].split(";")] == names
+
+
+@pytest.mark.gpu
+def test_config5_long_read_full_traceback(device, oracle, node_pool):
+    """BASELINE.json config 5: one 24,000-nt read (random + embedded genes + 10 % errors) against
+    profiles of 50..2000 nodes, window.c windows driven by the decoded hits, full trellis traceback.
+    Every window's null/alt cost is bit-exact with the oracle and every hit path identical."""
+    from deciphon_b200 import synth
+    from deciphon_b200.device import PAIR_DTYPE
+    rng = np.random.default_rng(2024)
+    sizes = [50, 200, 500, 1000, 2000]
+    profs = [synth.synth_profile(rng, K, node_pool, name=f"C5_{K}") for K in sizes]
+    parts = []
+    for p in profs:
+        cons = np.argmax(p.emission[:p.core_size, 20:84], axis=1)
+        cons = np.stack([cons // 16, (cons // 4) % 4, cons % 4], axis=1).reshape(-1).astype(np.uint8)
+        parts += [synth.random_read(rng, 600), cons[: min(len(cons), 3000)]]
+    x = synth.mutate(rng, np.concatenate(parts + [synth.random_read(rng, 25000)]), 0.10)[:24000]
+    assert len(x) == 24000
+    base = device.num_profiles
+    for p in profs:
+        device.add_profile(p)
+    device.set_reads([x])
+    nwin = nhit = 0
+    for pi, p in enumerate(profs):
+        costs = p.costs()
+        g = oracle.windows(len(x), p.core_size)
+        last = None
+        try:
+            w = next(g)
+            while True:
+                idx, a, b = w
+                win = np.ascontiguousarray(x[a:b])
+                pair = np.asarray([(base + pi, 0, a, b - a)], dtype=np.int32).view(PAIR_DTYPE).reshape(-1)
+                nul, alt = device.score_pairs(pair, True, False)
+                xt = oracle.xtrans(len(win), True, False)
+                assert nul[0].tobytes() == oracle.null(costs[0], xt, win).tobytes(), (p.core_size, idx)
+                assert alt[0].tobytes() == oracle.alt(costs, xt, win).tobytes(), (p.core_size, idx)
+                nwin += 1
+                last = None
+                lrt = oracle.lrt(nul[0], alt[0])
+                if np.isfinite(lrt) and lrt >= 0:
+                    talt, paths = device.trace_pairs(pair, True, False)
+                    ids, sz = oracle.path(costs, xt, win)
+                    assert np.array_equal(paths[0][0], ids) and np.array_equal(paths[0][1], sz), (p.core_size, idx)
+                    ext = oracle.hit_extent(ids, sz)
+                    if ext:
+                        last = ext[1] - 1
+                        nhit += 1
+                w = g.send(last)
+        except StopIteration:
+            pass
+    assert nwin >= 5 + 9 and nhit >= 4  # K = 50 alone yields ~10 windows of 2,500 nt
