@@ -35,6 +35,7 @@ SYMBOLS = [
     ("dcpgpu_hits_fetch", C.c_int, [_vp, _i64, _vp, C.POINTER(_i64)]),
     ("dcpgpu_last_cells", C.c_double, [_vp]),
     ("dcpgpu_last_kernel_ms", _f32, [_vp]),
+    ("dcpgpu_last_redo", _i64, [_vp]),
     ("dcpgpu_launch_count", _i64, [_vp]),
     ("dcpgpu_alu_peak", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     ("dcpgpu_trace_pairs", C.c_int, [_vp, _i64, _vp, _u32, _vp, _vp]),

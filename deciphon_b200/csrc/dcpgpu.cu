@@ -9,6 +9,7 @@
 #include "generic_kernel.cuh"
 #include "layout.cuh"
 #include "score_kernel.cuh"
+#include "strip_kernel.cuh"
 #include "trace_argmin.cuh"
 
 #include <algorithm>
@@ -115,6 +116,13 @@ struct dcpgpu_ctx
   size_t nsteps_cap = 0;
   float2 *d_tout = nullptr;
   size_t tout_cap = 0;
+  long long *d_redo = nullptr;
+  size_t redo_cap = 0;
+  Pair *d_redo_pairs = nullptr;
+  size_t redo_pairs_cap = 0;
+  long long *d_redo_order = nullptr, *d_redo_out = nullptr;
+  size_t redo_order_cap = 0, redo_out_cap = 0;
+  int64_t last_redo = 0;
   long long *d_hit_idx = nullptr;
   size_t hit_idx_cap = 0;
   float *d_dump = nullptr;
@@ -337,6 +345,8 @@ int sync_profiles(dcpgpu_ctx *ctx)
 // 9..20 = W = 2/4/8 warps per pair, Q = 5..8.
 constexpr int NCLASS = 21;
 
+ReadsView reads_view(dcpgpu_ctx const *ctx);
+
 int kernel_class(dcpgpu_ctx const *ctx, int profile)
 {
   ProfileDesc const &p = ctx->h_profiles[(size_t)profile];
@@ -401,6 +411,102 @@ int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 }
 
 int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a) { return launch_class_t<false>(ctx, cls, a); }
+
+template <int Q, int W>
+int launch_strip(dcpgpu_ctx *ctx, StripArgs const &a)
+{
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_strip_kernel<Q, W>, 32 * W, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned const grid = (unsigned)std::min<unsigned long long>(a.s.nitems, (unsigned long long)per_sm * ctx->sm_count);
+  score_strip_kernel<Q, W><<<grid, 32 * W, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+// classes 9..20 (W = 2/4/8): speculative strips first, the exact multi-warp kernel for the rest
+int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs const &a)
+{
+  switch (cls)
+  {
+  case 9: return launch_strip<5, 2>(ctx, a);
+  case 10: return launch_strip<6, 2>(ctx, a);
+  case 11: return launch_strip<7, 2>(ctx, a);
+  case 12: return launch_strip<8, 2>(ctx, a);
+  case 13: return launch_strip<5, 4>(ctx, a);
+  case 14: return launch_strip<6, 4>(ctx, a);
+  case 15: return launch_strip<7, 4>(ctx, a);
+  case 16: return launch_strip<8, 4>(ctx, a);
+  case 17: return launch_strip<5, 8>(ctx, a);
+  case 18: return launch_strip<6, 8>(ctx, a);
+  case 19: return launch_strip<7, 8>(ctx, a);
+  case 20: return launch_strip<8, 8>(ctx, a);
+  default: return fail(ctx, DCPGPU_EINVAL, "bad strip class");
+  }
+}
+
+// Pairs whose speculation failed (d_redo[0..n)): run them on the exact multi-warp kernels.
+// `to_pair` maps a result index to the window it stands for.
+template <class F>
+int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
+{
+  unsigned long long n = 0;
+  CU(cudaMemcpyAsync(&n, ctx->d_counters + 23, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->last_redo = (int64_t)n;
+  if (n == 0) return 0;
+  std::vector<long long> redo((size_t)n);
+  CU(cudaMemcpyAsync(redo.data(), ctx->d_redo, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::sort(redo.begin(), redo.end());
+  std::vector<Pair> rp((size_t)n);
+  std::vector<std::vector<long long>> bucket(NCLASS);
+  for (size_t i = 0; i < (size_t)n; ++i)
+  {
+    rp[i] = to_pair(redo[i]);
+    bucket[(size_t)kernel_class(ctx, rp[i].profile)].push_back((long long)i);
+  }
+  std::vector<long long> order, out_index;
+  size_t first[NCLASS + 1];
+  for (int c = 0; c < NCLASS; ++c)
+  {
+    first[c] = order.size();
+    for (long long i : bucket[(size_t)c])
+    {
+      order.push_back(i);
+      out_index.push_back(redo[(size_t)i]);
+    }
+  }
+  first[NCLASS] = order.size();
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_redo_pairs, ctx->redo_pairs_cap, (size_t)n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_redo_order, ctx->redo_order_cap, (size_t)n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_redo_out, ctx->redo_out_cap, (size_t)n))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_redo_pairs, rp.data(), (size_t)n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_redo_order, order.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_redo_out, out_index.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, 23 * sizeof(unsigned long long), ctx->stream));
+  for (int c = 9; c < NCLASS; ++c)
+  {
+    size_t const m = first[c + 1] - first[c];
+    if (!m) continue;
+    ScoreArgs a{};
+    a.profiles = ctx->d_profiles;
+    a.reads = reads_view(ctx);
+    a.xt = ctx->d_xt[flags & 3u];
+    a.pairs = ctx->d_redo_pairs;
+    a.order = ctx->d_redo_order + first[c];
+    a.out_index = ctx->d_redo_out + first[c];
+    a.nitems = m;
+    a.counter = ctx->d_counters + c;
+    a.out = ctx->d_out;
+    a.nhits = ctx->d_counters + 24;
+    if ((rc = launch_class(ctx, c, a))) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream)); // host vectors above
+  return 0;
+}
 
 // floats of scratch a generic-kernel launch over `nitems` pairs needs, and its grid
 template <bool TRACE>
@@ -600,6 +706,10 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_step_ids);
   cudaFree(ctx->d_dump);
   cudaFree(ctx->d_hit_idx);
+  cudaFree(ctx->d_redo);
+  cudaFree(ctx->d_redo_pairs);
+  cudaFree(ctx->d_redo_order);
+  cudaFree(ctx->d_redo_out);
   cudaFree(ctx->d_dump_off);
   cudaFree(ctx->d_tile_off);
   cudaFree(ctx->d_step_sz);
@@ -882,6 +992,8 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
 
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
+  if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
+  bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
 
@@ -905,9 +1017,23 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       g.s = a;
       if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
     }
+    else if (c >= 9)
+    { // speculative strips; failures are redone below
+      StripArgs sa{};
+      sa.s = a;
+      sa.redo = ctx->d_redo;
+      sa.nredo = ctx->d_counters + 23;
+      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
+      any_strip = true;
+    }
     else if ((rc = launch_class(ctx, c, a)))
       return rc;
   }
+  if (any_strip && (rc = redo_exact(ctx, flags, [&](long long oidx) {
+        dcpgpu_pair const &q = pairs[oidx];
+        return Pair{q.profile, q.seq, q.start, q.len};
+      })))
+    return rc;
   ctx->last_cells = cells;
   if ((rc = end_pass(ctx, npairs))) return rc;
   return dcpgpu_scores_fetch(ctx, npairs, null_cost, alt_cost);
@@ -954,6 +1080,12 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   }
   first[NCLASS] = flat.size();
   if ((rc = ensure(ctx, ctx->d_class_profiles, ctx->class_profiles_cap, flat.size()))) return rc;
+  {
+    size_t strip_items = 0;
+    for (int c = 9; c < NCLASS; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
+    if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, strip_items))) return rc;
+  }
+  bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -981,9 +1113,24 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       g.s = a;
       if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
     }
+    else if (c >= 9)
+    { // speculative strips; failures are redone below
+      StripArgs sa{};
+      sa.s = a;
+      sa.redo = ctx->d_redo;
+      sa.nredo = ctx->d_counters + 23;
+      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
+      any_strip = true;
+    }
     else if ((rc = launch_class(ctx, c, a)))
       return rc;
   }
+  if (any_strip && (rc = redo_exact(ctx, flags, [&](long long oidx) {
+        int const p = prof0 + (int)(oidx / nseq), sq = seq0 + (int)(oidx % nseq);
+        int const w = std::min(ctx->h_profiles[(size_t)p].K * 50, DCPGPU_MAX_WINDOW);
+        return Pair{p, sq, 0, std::min(w, ctx->h_seq_len[(size_t)sq])};
+      })))
+    return rc;
   ctx->last_cells = cells;
   return end_pass(ctx, (int64_t)npairs);
 }
@@ -1036,6 +1183,7 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
 }
 
 double dcpgpu_last_cells(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_cells : 0.0; }
+int64_t dcpgpu_last_redo(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_redo : 0; }
 int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx) { return ctx ? ctx->launches : 0; }
 
 float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx)

@@ -62,6 +62,7 @@ struct ScoreArgs
   // explicit mode: item -> pairs[order[item]]
   Pair const *pairs;
   long long const *order;
+  long long const *out_index;  // optional: where item's result goes (default: its pair index)
   unsigned long long nitems;
   unsigned long long *counter; // work-stealing cursor
   float2 *out;                 // {null cost, alt cost} per pair
@@ -710,6 +711,7 @@ __global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreAr
       sq = pr.seq;
       start = pr.start;
       len = pr.len;
+      if (a.out_index) oidx = a.out_index[item];
     }
     else
     {

@@ -167,6 +167,9 @@ class Device:
     def last_kernel_ms(self) -> float:
         return float(lib.dcpgpu_last_kernel_ms(self._h))
 
+    def last_redo(self) -> int:
+        return int(lib.dcpgpu_last_redo(self._h))
+
     def launch_count(self) -> int:
         return int(lib.dcpgpu_launch_count(self._h))
 

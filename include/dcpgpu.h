@@ -106,7 +106,8 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
 /* First window (window.c:13-37 from its initial state: [0, min(50K, 100000, |seq|)) ) of
  * every sequence in [seq0, seq1) against every profile in [prof0, prof1).  Pairs are
  * generated on the device, profile-major; results stay on the device until fetched.
- * Asynchronous on the context's stream. */
+ * Asynchronous on the context's stream unless profiles of more than 256 nodes are present
+ * (their speculative-strip kernels are followed by a host-side check of the redo queue). */
 int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq0, int32_t seq1,
                       uint32_t flags);
 /* Copy the last score pass' results to the host ([npairs] each, NULL = skip); synchronises. */
@@ -117,6 +118,9 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
 /* DP cells (sum of len*K) of the last score pass, and device ms of its kernels. */
 double dcpgpu_last_cells(dcpgpu_ctx const *ctx);
 float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx);
+/* Pairs of the last score pass whose speculative-strip run (profiles > 256 nodes) had to be
+ * redone by the exact multi-warp kernel (results are identical either way). */
+int64_t dcpgpu_last_redo(dcpgpu_ctx const *ctx);
 /* Cumulative number of kernels this library has launched on the context. */
 int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx);
 

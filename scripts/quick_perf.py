@@ -35,7 +35,7 @@ def main():
             best = min(best, dev.last_kernel_ms())
         cells = dev.last_cells()
         print(f"K={K:5d} profiles={nprof} reads={nreads} L={L} cells={cells:.3e} ms={best:9.3f} "
-              f"GCUPS={cells / best / 1e6:9.2f} hits={len(dev.hits_fetch())}", flush=True)
+              f"GCUPS={cells / best / 1e6:9.2f} hits={len(dev.hits_fetch())} redo={dev.last_redo()}", flush=True)
     dev.close()
 
 
