@@ -98,6 +98,13 @@ struct dcpgpu_ctx
   float *d_scratch = nullptr;
   size_t scratch_cap = 0; // floats
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // side streams: the per-class kernels of one pass are independent, so they are spread over these
+  // and the tail of one class overlaps the head of the next
+  static constexpr int NSIDE = 4;
+  cudaStream_t side[NSIDE] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
+  bool forked = false;
+  int side_next = 0;
   bool timed = false;
   double last_cells = 0;
   int64_t launches = 0; // cumulative count of kernels this library launched
@@ -118,6 +125,9 @@ struct dcpgpu_ctx
   size_t tout_cap = 0;
   long long *d_redo = nullptr;
   size_t redo_cap = 0;
+  Mail *d_col = nullptr; // boundary columns of the serial strip kernels
+  size_t col_cap = 0;
+  bool strip_concurrent = false; // DCPGPU_STRIP=concurrent: the CTA-per-pair strip kernel (A/B switch)
   Pair *d_redo_pairs = nullptr;
   size_t redo_pairs_cap = 0;
   long long *d_redo_order = nullptr, *d_redo_out = nullptr;
@@ -347,6 +357,35 @@ constexpr int NCLASS = 21;
 
 ReadsView reads_view(dcpgpu_ctx const *ctx);
 
+// stream the next class kernel goes to
+cudaStream_t launch_stream(dcpgpu_ctx *ctx)
+{
+  if (!ctx->forked) return ctx->stream;
+  cudaStream_t s = ctx->side[ctx->side_next];
+  ctx->side_next = (ctx->side_next + 1) % dcpgpu_ctx::NSIDE;
+  return s;
+}
+
+int fork_streams(dcpgpu_ctx *ctx)
+{
+  CU(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (auto s : ctx->side) CU(cudaStreamWaitEvent(s, ctx->ev_fork, 0));
+  ctx->forked = true;
+  ctx->side_next = 0;
+  return 0;
+}
+
+int join_streams(dcpgpu_ctx *ctx)
+{
+  ctx->forked = false;
+  for (int i = 0; i < dcpgpu_ctx::NSIDE; ++i)
+  {
+    CU(cudaEventRecord(ctx->ev_join[i], ctx->side[i]));
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+  }
+  return 0;
+}
+
 int kernel_class(dcpgpu_ctx const *ctx, int profile)
 {
   ProfileDesc const &p = ctx->h_profiles[(size_t)profile];
@@ -375,7 +414,7 @@ int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
   if (per_sm < 1) per_sm = 1;
   unsigned long long const want = (a.nitems + G - 1) / G;
   unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  score_reg_kernel<Q, W, DUMP><<<grid, T, SMEM, ctx->stream>>>(a);
+  score_reg_kernel<Q, W, DUMP><<<grid, T, SMEM, launch_stream(ctx)>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return 0;
@@ -419,31 +458,83 @@ int launch_strip(dcpgpu_ctx *ctx, StripArgs const &a)
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_strip_kernel<Q, W>, 32 * W, 0));
   if (per_sm < 1) per_sm = 1;
   unsigned const grid = (unsigned)std::min<unsigned long long>(a.s.nitems, (unsigned long long)per_sm * ctx->sm_count);
-  score_strip_kernel<Q, W><<<grid, 32 * W, 0, ctx->stream>>>(a);
+  score_strip_kernel<Q, W><<<grid, 32 * W, 0, launch_stream(ctx)>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return 0;
 }
 
-// classes 9..20 (W = 2/4/8): speculative strips first, the exact multi-warp kernel for the rest
-int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs const &a)
+template <int Q, int W>
+int sstrip_grid(dcpgpu_ctx *ctx, unsigned long long nitems, unsigned *grid)
 {
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_sstrip_kernel<Q, W>, 32 * SSTRIP_WARPS, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned long long const want = (nitems + SSTRIP_WARPS - 1) / SSTRIP_WARPS;
+  *grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
+  return 0;
+}
+
+template <int Q, int W>
+int launch_sstrip(dcpgpu_ctx *ctx, StripArgs const &a, unsigned grid)
+{
+  score_sstrip_kernel<Q, W><<<grid, 32 * SSTRIP_WARPS, 0, launch_stream(ctx)>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+// f(Q, W) for a strip class 9..20 (W = 2/4/8 x Q = 5..8)
+template <class F>
+int strip_dispatch(dcpgpu_ctx *ctx, int cls, F &&f)
+{
+#define DCP_SC(c, Q_, W_) \
+  case c: return f(std::integral_constant<int, Q_>{}, std::integral_constant<int, W_>{});
   switch (cls)
   {
-  case 9: return launch_strip<5, 2>(ctx, a);
-  case 10: return launch_strip<6, 2>(ctx, a);
-  case 11: return launch_strip<7, 2>(ctx, a);
-  case 12: return launch_strip<8, 2>(ctx, a);
-  case 13: return launch_strip<5, 4>(ctx, a);
-  case 14: return launch_strip<6, 4>(ctx, a);
-  case 15: return launch_strip<7, 4>(ctx, a);
-  case 16: return launch_strip<8, 4>(ctx, a);
-  case 17: return launch_strip<5, 8>(ctx, a);
-  case 18: return launch_strip<6, 8>(ctx, a);
-  case 19: return launch_strip<7, 8>(ctx, a);
-  case 20: return launch_strip<8, 8>(ctx, a);
+    DCP_SC(9, 5, 2) DCP_SC(10, 6, 2) DCP_SC(11, 7, 2) DCP_SC(12, 8, 2)
+    DCP_SC(13, 5, 4) DCP_SC(14, 6, 4) DCP_SC(15, 7, 4) DCP_SC(16, 8, 4)
+    DCP_SC(17, 5, 8) DCP_SC(18, 6, 8) DCP_SC(19, 7, 8) DCP_SC(20, 8, 8)
   default: return fail(ctx, DCPGPU_EINVAL, "bad strip class");
   }
+#undef DCP_SC
+}
+
+// classes 9..20: speculative strips first, the exact multi-warp kernel for the pairs that fail
+int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs const &a, unsigned grid)
+{
+  return strip_dispatch(ctx, cls, [&](auto q, auto w) {
+    if (ctx->strip_concurrent) return launch_strip<decltype(q)::value, decltype(w)::value>(ctx, a);
+    return launch_sstrip<decltype(q)::value, decltype(w)::value>(ctx, a, grid);
+  });
+}
+
+// Grids of the serial strip kernels of one pass and their slices of the boundary-column buffer
+// (classes run concurrently, so each needs its own): count[c] items of windows up to maxlen.
+struct StripPlan
+{
+  unsigned grid[NCLASS] = {};
+  size_t col_off[NCLASS] = {};
+  size_t stride = 0;
+};
+
+int plan_strips(dcpgpu_ctx *ctx, unsigned long long const *count, int maxlen, StripPlan *plan)
+{
+  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
+  size_t total = 0;
+  for (int c = 9; c < NCLASS; ++c)
+  {
+    if (!count[c]) continue;
+    unsigned long long const n = count[c];
+    int rc = strip_dispatch(ctx, c, [&](auto q, auto w) {
+      return sstrip_grid<decltype(q)::value, decltype(w)::value>(ctx, n, &plan->grid[c]);
+    });
+    if (rc) return rc;
+    plan->col_off[c] = total;
+    total += (size_t)plan->grid[c] * SSTRIP_WARPS * plan->stride;
+  }
+  if (ctx->strip_concurrent || !total) return 0;
+  return ensure(ctx, ctx->d_col, ctx->col_cap, total);
 }
 
 // Pairs whose speculation failed (d_redo[0..n)): run them on the exact multi-warp kernels.
@@ -487,6 +578,7 @@ int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
   CU(cudaMemcpyAsync(ctx->d_redo_order, order.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_redo_out, out_index.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_counters, 0, 23 * sizeof(unsigned long long), ctx->stream));
+  if ((rc = fork_streams(ctx))) return rc;
   for (int c = 9; c < NCLASS; ++c)
   {
     size_t const m = first[c + 1] - first[c];
@@ -504,6 +596,7 @@ int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
     a.nhits = ctx->d_counters + 24;
     if ((rc = launch_class(ctx, c, a))) return rc;
   }
+  if ((rc = join_streams(ctx))) return rc;
   CU(cudaStreamSynchronize(ctx->stream)); // host vectors above
   return 0;
 }
@@ -532,7 +625,7 @@ int launch_generic(dcpgpu_ctx *ctx, GenArgs a, int max_K)
   if ((rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, need))) return rc;
   a.scratch = ctx->d_scratch;
   a.scratch_stride = (size_t)19 * ((max_K + 31) & ~31);
-  generic_kernel<TRACE><<<grid, GEN_THREADS, 0, ctx->stream>>>(a);
+  generic_kernel<TRACE><<<grid, GEN_THREADS, 0, launch_stream(ctx)>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return 0;
@@ -577,7 +670,9 @@ int begin_pass(dcpgpu_ctx *ctx, size_t npairs)
   if (rc) return rc;
   if ((rc = ensure(ctx, ctx->d_out, ctx->out_cap, npairs))) return rc;
   CU(cudaMemsetAsync(ctx->d_counters, 0, 26 * sizeof(unsigned long long), ctx->stream));
+  ctx->forked = false;
   ctx->last_cells = 0;
+  ctx->last_redo = 0;
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
   return 0;
 }
@@ -661,10 +756,20 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   dcpgpu_ctx *ctx = new (std::nothrow) dcpgpu_ctx;
   if (!ctx) return DCPGPU_ENOMEM;
   ctx->device = device;
+  {
+    char const *v = std::getenv("DCPGPU_STRIP");
+    ctx->strip_concurrent = v && std::strcmp(v, "concurrent") == 0;
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  for (int i = 0; i < dcpgpu_ctx::NSIDE; ++i)
+  {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
+  }
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_counters), 32 * sizeof(unsigned long long));
   if (e != cudaSuccess)
@@ -707,6 +812,7 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_dump);
   cudaFree(ctx->d_hit_idx);
   cudaFree(ctx->d_redo);
+  cudaFree(ctx->d_col);
   cudaFree(ctx->d_redo_pairs);
   cudaFree(ctx->d_redo_order);
   cudaFree(ctx->d_redo_out);
@@ -715,6 +821,12 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_step_sz);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < dcpgpu_ctx::NSIDE; ++i)
+  {
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+  }
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -993,12 +1105,20 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
+  StripPlan plan;
+  {
+    unsigned long long count[NCLASS];
+    for (int c = 0; c < NCLASS; ++c) count[c] = first[c + 1] - first[c];
+    if ((rc = plan_strips(ctx, count, maxlen, &plan))) return rc;
+  }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
 
-  for (int c = 0; c < NCLASS; ++c)
+  if ((rc = fork_streams(ctx))) return rc;
+  for (int ci = 0; ci < NCLASS; ++ci)
   {
+    int const c = ci ? NCLASS - ci : 0; // longest pairs first: their tail hides under the rest
     size_t const n = first[c + 1] - first[c];
     if (!n) continue;
     ScoreArgs a{};
@@ -1023,12 +1143,15 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       sa.s = a;
       sa.redo = ctx->d_redo;
       sa.nredo = ctx->d_counters + 23;
-      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
+      sa.col = ctx->d_col + plan.col_off[c];
+      sa.col_stride = plan.stride;
+      if ((rc = launch_strip_class(ctx, c, sa, plan.grid[c]))) return rc;
       any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
       return rc;
   }
+  if ((rc = join_streams(ctx))) return rc;
   if (any_strip && (rc = redo_exact(ctx, flags, [&](long long oidx) {
         dcpgpu_pair const &q = pairs[oidx];
         return Pair{q.profile, q.seq, q.start, q.len};
@@ -1085,14 +1208,22 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     for (int c = 9; c < NCLASS; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
     if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, strip_items))) return rc;
   }
+  StripPlan plan;
+  {
+    unsigned long long count[NCLASS];
+    for (int c = 0; c < NCLASS; ++c) count[c] = (unsigned long long)(first[c + 1] - first[c]) * (unsigned long long)nseq;
+    if ((rc = plan_strips(ctx, count, ctx->maxlen, &plan))) return rc;
+  }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
 
-  // large classes first: the generic kernel (big K) has the longest tail
-  for (int c = 0; c < NCLASS; ++c)
+  // longest pairs first (generic, then W = 8 .. 1): their tail hides under the classes that follow
+  if ((rc = fork_streams(ctx))) return rc;
+  for (int ci = 0; ci < NCLASS; ++ci)
   {
+    int const c = ci ? NCLASS - ci : 0;
     size_t const n = first[c + 1] - first[c];
     if (!n) continue;
     ScoreArgs a{};
@@ -1119,12 +1250,15 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       sa.s = a;
       sa.redo = ctx->d_redo;
       sa.nredo = ctx->d_counters + 23;
-      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
+      sa.col = ctx->d_col + plan.col_off[c];
+      sa.col_stride = plan.stride;
+      if ((rc = launch_strip_class(ctx, c, sa, plan.grid[c]))) return rc;
       any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
       return rc;
   }
+  if ((rc = join_streams(ctx))) return rc;
   if (any_strip && (rc = redo_exact(ctx, flags, [&](long long oidx) {
         int const p = prof0 + (int)(oidx / nseq), sq = seq0 + (int)(oidx % nseq);
         int const w = std::min(ctx->h_profiles[(size_t)p].K * 50, DCPGPU_MAX_WINDOW);
