@@ -46,6 +46,7 @@ SYMBOLS = [
 
 MULTI_HITS = 1
 HMMER3_COMPAT = 2
+KEEP_TRELLIS = 4
 
 
 class DcpGpuError(RuntimeError):

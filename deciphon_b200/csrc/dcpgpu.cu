@@ -11,6 +11,7 @@
 #include "score_kernel.cuh"
 #include "strip_kernel.cuh"
 #include "trace_argmin.cuh"
+#include "trace_walk.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -125,9 +126,6 @@ struct dcpgpu_ctx
   size_t tout_cap = 0;
   long long *d_redo = nullptr;
   size_t redo_cap = 0;
-  Mail *d_col = nullptr; // boundary columns of the serial strip kernels
-  size_t col_cap = 0;
-  bool strip_concurrent = false; // DCPGPU_STRIP=concurrent: the CTA-per-pair strip kernel (A/B switch)
   Pair *d_redo_pairs = nullptr;
   size_t redo_pairs_cap = 0;
   long long *d_redo_order = nullptr, *d_redo_out = nullptr;
@@ -146,6 +144,13 @@ struct dcpgpu_ctx
   std::vector<long long> t_xnode_off, t_node_off;
   std::vector<int> t_nsteps;
   bool traced = false;
+  // paths-only trace route (trace_walk.cuh): steps in the order the walks finished
+  uint16_t *d_lz_ids = nullptr;
+  size_t lz_ids_cap = 0;
+  uint8_t *d_lz_sz = nullptr;
+  size_t lz_sz_cap = 0;
+  long long *d_lz_off = nullptr; // per pair; -1 = traced through a kept trellis
+  size_t lz_off_cap = 0;
 };
 
 namespace {
@@ -464,26 +469,6 @@ int launch_strip(dcpgpu_ctx *ctx, StripArgs const &a)
   return 0;
 }
 
-template <int Q, int W>
-int sstrip_grid(dcpgpu_ctx *ctx, unsigned long long nitems, unsigned *grid)
-{
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_sstrip_kernel<Q, W>, 32 * SSTRIP_WARPS, 0));
-  if (per_sm < 1) per_sm = 1;
-  unsigned long long const want = (nitems + SSTRIP_WARPS - 1) / SSTRIP_WARPS;
-  *grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  return 0;
-}
-
-template <int Q, int W>
-int launch_sstrip(dcpgpu_ctx *ctx, StripArgs const &a, unsigned grid)
-{
-  score_sstrip_kernel<Q, W><<<grid, 32 * SSTRIP_WARPS, 0, launch_stream(ctx)>>>(a);
-  CU(cudaGetLastError());
-  ctx->launches += 1;
-  return 0;
-}
-
 // f(Q, W) for a strip class 9..20 (W = 2/4/8 x Q = 5..8)
 template <class F>
 int strip_dispatch(dcpgpu_ctx *ctx, int cls, F &&f)
@@ -501,40 +486,11 @@ int strip_dispatch(dcpgpu_ctx *ctx, int cls, F &&f)
 }
 
 // classes 9..20: speculative strips first, the exact multi-warp kernel for the pairs that fail
-int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs const &a, unsigned grid)
+int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs const &a)
 {
   return strip_dispatch(ctx, cls, [&](auto q, auto w) {
-    if (ctx->strip_concurrent) return launch_strip<decltype(q)::value, decltype(w)::value>(ctx, a);
-    return launch_sstrip<decltype(q)::value, decltype(w)::value>(ctx, a, grid);
+    return launch_strip<decltype(q)::value, decltype(w)::value>(ctx, a);
   });
-}
-
-// Grids of the serial strip kernels of one pass and their slices of the boundary-column buffer
-// (classes run concurrently, so each needs its own): count[c] items of windows up to maxlen.
-struct StripPlan
-{
-  unsigned grid[NCLASS] = {};
-  size_t col_off[NCLASS] = {};
-  size_t stride = 0;
-};
-
-int plan_strips(dcpgpu_ctx *ctx, unsigned long long const *count, int maxlen, StripPlan *plan)
-{
-  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
-  size_t total = 0;
-  for (int c = 9; c < NCLASS; ++c)
-  {
-    if (!count[c]) continue;
-    unsigned long long const n = count[c];
-    int rc = strip_dispatch(ctx, c, [&](auto q, auto w) {
-      return sstrip_grid<decltype(q)::value, decltype(w)::value>(ctx, n, &plan->grid[c]);
-    });
-    if (rc) return rc;
-    plan->col_off[c] = total;
-    total += (size_t)plan->grid[c] * SSTRIP_WARPS * plan->stride;
-  }
-  if (ctx->strip_concurrent || !total) return 0;
-  return ensure(ctx, ctx->d_col, ctx->col_cap, total);
 }
 
 // Pairs whose speculation failed (d_redo[0..n)): run them on the exact multi-warp kernels.
@@ -756,10 +712,6 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   dcpgpu_ctx *ctx = new (std::nothrow) dcpgpu_ctx;
   if (!ctx) return DCPGPU_ENOMEM;
   ctx->device = device;
-  {
-    char const *v = std::getenv("DCPGPU_STRIP");
-    ctx->strip_concurrent = v && std::strcmp(v, "concurrent") == 0;
-  }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
@@ -806,13 +758,15 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_xnode_off);
   cudaFree(ctx->d_node_off);
   cudaFree(ctx->d_step_off);
+  cudaFree(ctx->d_lz_ids);
+  cudaFree(ctx->d_lz_sz);
+  cudaFree(ctx->d_lz_off);
   cudaFree(ctx->d_nsteps);
   cudaFree(ctx->d_tout);
   cudaFree(ctx->d_step_ids);
   cudaFree(ctx->d_dump);
   cudaFree(ctx->d_hit_idx);
   cudaFree(ctx->d_redo);
-  cudaFree(ctx->d_col);
   cudaFree(ctx->d_redo_pairs);
   cudaFree(ctx->d_redo_order);
   cudaFree(ctx->d_redo_out);
@@ -1105,12 +1059,6 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
-  StripPlan plan;
-  {
-    unsigned long long count[NCLASS];
-    for (int c = 0; c < NCLASS; ++c) count[c] = first[c + 1] - first[c];
-    if ((rc = plan_strips(ctx, count, maxlen, &plan))) return rc;
-  }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -1143,9 +1091,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       sa.s = a;
       sa.redo = ctx->d_redo;
       sa.nredo = ctx->d_counters + 23;
-      sa.col = ctx->d_col + plan.col_off[c];
-      sa.col_stride = plan.stride;
-      if ((rc = launch_strip_class(ctx, c, sa, plan.grid[c]))) return rc;
+      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
       any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
@@ -1208,12 +1154,6 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     for (int c = 9; c < NCLASS; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
     if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, strip_items))) return rc;
   }
-  StripPlan plan;
-  {
-    unsigned long long count[NCLASS];
-    for (int c = 0; c < NCLASS; ++c) count[c] = (unsigned long long)(first[c + 1] - first[c]) * (unsigned long long)nseq;
-    if ((rc = plan_strips(ctx, count, ctx->maxlen, &plan))) return rc;
-  }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
@@ -1250,9 +1190,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       sa.s = a;
       sa.redo = ctx->d_redo;
       sa.nredo = ctx->d_counters + 23;
-      sa.col = ctx->d_col + plan.col_off[c];
-      sa.col_stride = plan.stride;
-      if ((rc = launch_strip_class(ctx, c, sa, plan.grid[c]))) return rc;
+      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
       any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
@@ -1349,13 +1287,17 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     ctx->traced = true;
     return 0;
   }
-  int maxK = 1;
+  // The full trellis is only materialised on request (DCPGPU_KEEP_TRELLIS) and for profiles the
+  // register kernels cannot run; all other pairs are walked straight from the dumped values.
+  bool const keep = (flags & DCPGPU_KEEP_TRELLIS) != 0;
+  std::vector<long long> slot_off((size_t)npairs + 1, 0); // lazily walked paths: generous slots
   for (int64_t i = 0; i < npairs; ++i)
   {
     int const K = ctx->h_profiles[(size_t)pairs[i].profile].K;
-    maxK = std::max(maxK, K);
-    ctx->t_xnode_off[(size_t)i + 1] = ctx->t_xnode_off[(size_t)i] + (pairs[i].len + 1);
-    ctx->t_node_off[(size_t)i + 1] = ctx->t_node_off[(size_t)i] + (long long)(pairs[i].len + 1) * K;
+    bool const trellis = keep || kernel_class(ctx, pairs[i].profile) == 0;
+    ctx->t_xnode_off[(size_t)i + 1] = ctx->t_xnode_off[(size_t)i] + (trellis ? pairs[i].len + 1 : 0);
+    ctx->t_node_off[(size_t)i + 1] = ctx->t_node_off[(size_t)i] + (trellis ? (long long)(pairs[i].len + 1) * K : 0);
+    slot_off[(size_t)i + 1] = slot_off[(size_t)i] + (trellis ? 0 : (long long)pairs[i].len + 2 * (long long)K + 64);
   }
   size_t const n = (size_t)npairs;
   if ((rc = ensure(ctx, ctx->d_tpairs, ctx->tpairs_cap, n))) return rc;
@@ -1365,6 +1307,14 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_node_off, ctx->node_off_cap, n + 1))) return rc;
   if ((rc = ensure(ctx, ctx->d_nsteps, ctx->nsteps_cap, n))) return rc;
   if ((rc = ensure(ctx, ctx->d_tout, ctx->tout_cap, n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_lz_off, ctx->lz_off_cap, n + 1))) return rc;
+  if (slot_off[n])
+  {
+    if ((rc = ensure(ctx, ctx->d_lz_ids, ctx->lz_ids_cap, (size_t)slot_off[n]))) return rc;
+    if ((rc = ensure(ctx, ctx->d_lz_sz, ctx->lz_sz_cap, (size_t)slot_off[n]))) return rc;
+  }
+  CU(cudaMemcpyAsync(ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + 22, 0, sizeof(unsigned long long), ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -1409,83 +1359,132 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
         ctx->dump_cap = need;
       }
     }
-    for (int cls = NCLASS - 1; cls >= 1; --cls)
-    {
-      std::vector<long long> const &list = by_class[(size_t)cls];
-      size_t c0 = 0;
-      while (c0 < list.size())
+    auto run_fast = [&]() -> int {
+      for (int cls = NCLASS - 1; cls >= 1; --cls)
       {
-        // chunk [c0, c1) bounded by the dump budget
-        size_t c1 = c0, floats = 0;
-        while (c1 < list.size())
+        std::vector<long long> const &list = by_class[(size_t)cls];
+        size_t c0 = 0;
+        while (c0 < list.size())
         {
-          dcpgpu_pair const &pr = pairs[list[c1]];
-          size_t const f = DumpView::floats(pr.len, ctx->h_profiles[(size_t)pr.profile].Kpad);
-          if (c1 > c0 && floats + f > budget) break;
-          dump_off[(size_t)list[c1]] = (long long)floats;
-          floats += f;
-          ++c1;
+          // chunk [c0, c1) bounded by the dump budget
+          size_t c1 = c0, floats = 0;
+          while (c1 < list.size())
+          {
+            dcpgpu_pair const &pr = pairs[list[c1]];
+            size_t const f = DumpView::floats(pr.len, ctx->h_profiles[(size_t)pr.profile].Kpad);
+            if (c1 > c0 && floats + f > budget) break;
+            dump_off[(size_t)list[c1]] = (long long)floats;
+            floats += f;
+            ++c1;
+          }
+          size_t const cn = c1 - c0;
+          if (floats > ctx->dump_cap) return fail(ctx, DCPGPU_ESTATE, "trace: dump buffer too small (internal error)");
+          std::vector<long long> tile_off(cn + 1, 0), doff(cn);
+          for (size_t i = 0; i < cn; ++i)
+          {
+            tile_off[i + 1] = tile_off[i] + (pairs[list[c0 + i]].len + ARGMIN_ROWS - 1) / ARGMIN_ROWS;
+            doff[i] = dump_off[(size_t)list[c0 + i]];
+          }
+          if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, cn))) return rc;
+          if ((rc = ensure(ctx, ctx->d_tile_off, ctx->tile_off_cap, cn + 1))) return rc;
+          CU(cudaMemcpyAsync(ctx->d_order, list.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+          CU(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (cn + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+          // dump offsets are indexed by the item's position in this launch
+          CU(cudaMemcpyAsync(ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+          CU(cudaMemsetAsync(ctx->d_counters + cls, 0, sizeof(unsigned long long), ctx->stream));
+          ScoreArgs sa{};
+          sa.profiles = ctx->d_profiles;
+          sa.reads = reads_view(ctx);
+          sa.xt = ctx->d_xt[flags & 3u];
+          sa.pairs = ctx->d_tpairs;
+          sa.order = ctx->d_order;
+          sa.nitems = cn;
+          sa.counter = ctx->d_counters + cls;
+          sa.out = ctx->d_tout;
+          sa.nhits = ctx->d_counters + 27;
+          sa.dump = ctx->d_dump;
+          sa.dump_off = ctx->d_dump_off;
+          if ((rc = launch_class_t<true>(ctx, cls, sa))) return rc;
+          if (!keep)
+          { // paths only: walk the dumped values directly
+            LazyWalkArgs z{};
+            z.profiles = ctx->d_profiles;
+            z.reads = reads_view(ctx);
+            z.xt = ctx->d_xt[flags & 3u];
+            z.pairs = ctx->d_tpairs;
+            z.order = ctx->d_order;
+            z.nitems = (long long)cn;
+            z.dump = ctx->d_dump;
+            z.dump_off = ctx->d_dump_off;
+            z.nsteps = ctx->d_nsteps;
+            z.slot_off = ctx->d_lz_off;
+            z.overflow = ctx->d_counters + 22;
+            z.ids = ctx->d_lz_ids;
+            z.sizes = ctx->d_lz_sz;
+            lazy_walk_kernel<<<(unsigned)((cn + LAZY_WARPS - 1) / LAZY_WARPS), 32 * LAZY_WARPS, 0, ctx->stream>>>(z);
+            CU(cudaGetLastError());
+            ctx->launches += 1;
+            CU(cudaStreamSynchronize(ctx->stream));
+            c0 = c1;
+            continue;
+          }
+          ArgminArgs g{};
+          g.profiles = ctx->d_profiles;
+          g.reads = reads_view(ctx);
+          g.xt = ctx->d_xt[flags & 3u];
+          g.pairs = ctx->d_tpairs;
+          g.order = ctx->d_order;
+          g.tile_off = ctx->d_tile_off;
+          g.nitems = (long long)cn;
+          g.dump = ctx->d_dump;
+          g.dump_off = ctx->d_dump_off;
+          g.xnodes = ctx->d_xnodes;
+          g.nodes = ctx->d_nodes;
+          g.xnode_off = ctx->d_xnode_off;
+          g.node_off = ctx->d_node_off;
+          trace_argmin_kernel<<<(unsigned)tile_off[cn], ARGMIN_THREADS, 0, ctx->stream>>>(g);
+          CU(cudaGetLastError());
+          WalkCountArgs w{};
+          w.profiles = ctx->d_profiles;
+          w.pairs = ctx->d_tpairs;
+          w.order = ctx->d_order;
+          w.nitems = (long long)cn;
+          w.xnodes = ctx->d_xnodes;
+          w.nodes = ctx->d_nodes;
+          w.xnode_off = ctx->d_xnode_off;
+          w.node_off = ctx->d_node_off;
+          w.nsteps = ctx->d_nsteps;
+          walk_count_kernel<<<(unsigned)((cn + 63) / 64), 64, 0, ctx->stream>>>(w);
+          CU(cudaGetLastError());
+          ctx->launches += 2;
+          // host vectors and the device order/tile buffers are reused by the next chunk
+          CU(cudaStreamSynchronize(ctx->stream));
+          c0 = c1;
         }
-        size_t const cn = c1 - c0;
-        if (floats > ctx->dump_cap) return fail(ctx, DCPGPU_ESTATE, "trace: dump buffer too small (internal error)");
-        std::vector<long long> tile_off(cn + 1, 0), doff(cn);
-        for (size_t i = 0; i < cn; ++i)
-        {
-          tile_off[i + 1] = tile_off[i] + (pairs[list[c0 + i]].len + ARGMIN_ROWS - 1) / ARGMIN_ROWS;
-          doff[i] = dump_off[(size_t)list[c0 + i]];
-        }
-        if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, cn))) return rc;
-        if ((rc = ensure(ctx, ctx->d_tile_off, ctx->tile_off_cap, cn + 1))) return rc;
-        CU(cudaMemcpyAsync(ctx->d_order, list.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (cn + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        // dump offsets are indexed by the item's position in this launch
-        CU(cudaMemcpyAsync(ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_counters + cls, 0, sizeof(unsigned long long), ctx->stream));
-        ScoreArgs sa{};
-        sa.profiles = ctx->d_profiles;
-        sa.reads = reads_view(ctx);
-        sa.xt = ctx->d_xt[flags & 3u];
-        sa.pairs = ctx->d_tpairs;
-        sa.order = ctx->d_order;
-        sa.nitems = cn;
-        sa.counter = ctx->d_counters + cls;
-        sa.out = ctx->d_tout;
-        sa.nhits = ctx->d_counters + 27;
-        sa.dump = ctx->d_dump;
-        sa.dump_off = ctx->d_dump_off;
-        if ((rc = launch_class_t<true>(ctx, cls, sa))) return rc;
-        ArgminArgs g{};
-        g.profiles = ctx->d_profiles;
-        g.reads = reads_view(ctx);
-        g.xt = ctx->d_xt[flags & 3u];
-        g.pairs = ctx->d_tpairs;
-        g.order = ctx->d_order;
-        g.tile_off = ctx->d_tile_off;
-        g.nitems = (long long)cn;
-        g.dump = ctx->d_dump;
-        g.dump_off = ctx->d_dump_off;
-        g.xnodes = ctx->d_xnodes;
-        g.nodes = ctx->d_nodes;
-        g.xnode_off = ctx->d_xnode_off;
-        g.node_off = ctx->d_node_off;
-        trace_argmin_kernel<<<(unsigned)tile_off[cn], ARGMIN_THREADS, 0, ctx->stream>>>(g);
-        CU(cudaGetLastError());
-        WalkCountArgs w{};
-        w.profiles = ctx->d_profiles;
-        w.pairs = ctx->d_tpairs;
-        w.order = ctx->d_order;
-        w.nitems = (long long)cn;
-        w.xnodes = ctx->d_xnodes;
-        w.nodes = ctx->d_nodes;
-        w.xnode_off = ctx->d_xnode_off;
-        w.node_off = ctx->d_node_off;
-        w.nsteps = ctx->d_nsteps;
-        walk_count_kernel<<<(unsigned)((cn + 63) / 64), 64, 0, ctx->stream>>>(w);
-        CU(cudaGetLastError());
-        ctx->launches += 2;
-        // host vectors and the device order/tile buffers are reused by the next chunk
+      }
+      return 0;
+    };
+    if ((rc = run_fast())) return rc;
+    if (!keep)
+    { // a path that outgrew its slot was only counted: give every pair its exact size and redo
+      unsigned long long over = 0;
+      CU(cudaMemcpyAsync(&over, ctx->d_counters + 22, sizeof over, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if (over)
+      {
+        CU(cudaMemcpyAsync(ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        c0 = c1;
+        for (size_t i = 0; i < n; ++i)
+        {
+          long long const have = slot_off[i + 1] - slot_off[i];
+          slot_off[i + 1] = slot_off[i] + (have ? std::max<long long>(have, ctx->t_nsteps[i]) : 0);
+        }
+        if ((rc = ensure(ctx, ctx->d_lz_ids, ctx->lz_ids_cap, (size_t)slot_off[n]))) return rc;
+        if ((rc = ensure(ctx, ctx->d_lz_sz, ctx->lz_sz_cap, (size_t)slot_off[n]))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_counters + 22, 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); // slot_off is re-read by nothing after this, but keep it simple
+        if ((rc = run_fast())) return rc;
       }
     }
   }
@@ -1591,12 +1590,9 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
   if ((rc = ensure(ctx, ctx->d_step_sz, ctx->step_sz_cap, total))) return rc;
   uint16_t *d_ids = ctx->d_step_ids;
   uint8_t *d_sz = ctx->d_step_sz;
-  cudaError_t e;
-  std::vector<uint16_t> h_ids(total);
-  std::vector<uint8_t> h_sz(total);
-  e = cudaMemcpyAsync(ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream);
-  if (e == cudaSuccess)
-  {
+  CU(cudaMemcpyAsync(ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->t_node_off[n] > 0)
+  { // pairs traced through a trellis: second back-walk, in path order
     WalkArgs w{};
     w.profiles = ctx->d_profiles;
     w.pairs = ctx->d_tpairs;
@@ -1610,13 +1606,37 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
     w.ids = d_ids;
     w.sizes = d_sz;
     walk_write_kernel<<<(unsigned)((n + 63) / 64), 64, 0, ctx->stream>>>(w);
-    e = cudaGetLastError();
+    CU(cudaGetLastError());
     ctx->launches += 1;
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e != cudaSuccess) return fail_cuda(ctx, e, "trace_fetch");
+  { // pairs walked from the dumped values: move each path to its place
+    GatherArgs g{};
+    g.npairs = (long long)n;
+    g.nsteps = ctx->d_nsteps;
+    g.src_off = ctx->d_lz_off;
+    g.dst_off = ctx->d_step_off;
+    g.src_ids = ctx->d_lz_ids;
+    g.src_sizes = ctx->d_lz_sz;
+    g.ids = d_ids;
+    g.sizes = d_sz;
+    gather_steps_kernel<<<(unsigned)((n + 7) / 8), 256, 0, ctx->stream>>>(g);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+  }
+  bool compact = true; // the usual placement: paths back to back in pair order
+  for (size_t i = 0; i < n && compact; ++i) compact = offsets[i] == offsets[0] + off[i];
+  if (compact)
+  {
+    CU(cudaMemcpyAsync(state_ids + offsets[0], d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(seqsizes + offsets[0], d_sz, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  std::vector<uint16_t> h_ids(total);
+  std::vector<uint8_t> h_sz(total);
+  CU(cudaMemcpyAsync(h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n; ++i)
   {
     std::memcpy(state_ids + offsets[i], h_ids.data() + off[i], (size_t)ctx->t_nsteps[i] * sizeof(uint16_t));
@@ -1631,6 +1651,7 @@ int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t 
   if (i < 0 || (size_t)i >= ctx->t_pairs.size()) return fail(ctx, DCPGPU_EINVAL, "trace_trellis: bad index");
   CU(cudaSetDevice(ctx->device));
   size_t const nx = (size_t)(ctx->t_xnode_off[(size_t)i + 1] - ctx->t_xnode_off[(size_t)i]);
+  if (nx == 0) return fail(ctx, DCPGPU_ESTATE, "trace_trellis: trace_pairs ran without DCPGPU_KEEP_TRELLIS");
   size_t const nn = (size_t)(ctx->t_node_off[(size_t)i + 1] - ctx->t_node_off[(size_t)i]);
   if (xnodes)
     CU(cudaMemcpyAsync(xnodes, ctx->d_xnodes + ctx->t_xnode_off[(size_t)i], nx * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -602,7 +602,7 @@ __global__ void walk_write_kernel(WalkArgs a)
   long long const i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= a.npairs) return;
   int const n = a.nsteps[i];
-  if (n <= 0) return;
+  if (n <= 0 || a.node_off[i + 1] == a.node_off[i]) return; // no trellis kept: walked lazily
   Pair const pr = a.pairs[i];
   int const K = a.profiles[pr.profile].K;
   trellis_walk(K, pr.len, a.xnodes + a.xnode_off[i], a.nodes + a.node_off[i], n,

@@ -11,13 +11,14 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import HMMER3_COMPAT, MULTI_HITS, DcpGpuError, lib
+from ._lib import HMMER3_COMPAT, KEEP_TRELLIS, MULTI_HITS, DcpGpuError, lib
 
 PAIR_DTYPE = np.dtype([("profile", "<i4"), ("seq", "<i4"), ("start", "<i4"), ("len", "<i4")])
 
 
-def flags_of(multi_hits: bool, hmmer3_compat: bool) -> int:
-    return (MULTI_HITS if multi_hits else 0) | (HMMER3_COMPAT if hmmer3_compat else 0)
+def flags_of(multi_hits: bool, hmmer3_compat: bool, keep_trellis: bool = False) -> int:
+    return ((MULTI_HITS if multi_hits else 0) | (HMMER3_COMPAT if hmmer3_compat else 0)
+            | (KEEP_TRELLIS if keep_trellis else 0))
 
 
 def _ptr(a):
@@ -180,7 +181,7 @@ class Device:
         return v.value
 
     # -- trace pass ----------------------------------------------------------------------
-    def trace_pairs_flat(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):
+    def trace_pairs_flat(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False, keep_trellis=False):
         """Returns (alt_cost[n], offsets[n+1], state_ids uint16[total], seqsizes uint8[total])."""
         pairs = np.ascontiguousarray(pairs)
         if pairs.dtype != PAIR_DTYPE:
@@ -188,7 +189,8 @@ class Device:
         n = pairs.shape[0]
         alt = np.empty(n, dtype=np.float32)
         nsteps = np.zeros(n, dtype=np.int32)
-        self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs), flags_of(multi_hits, hmmer3_compat),
+        self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs),
+                                           flags_of(multi_hits, hmmer3_compat, keep_trellis),
                                            _ptr(alt), _ptr(nsteps)))
         off = np.zeros(n + 1, dtype=np.int64)
         off[1:] = np.cumsum(nsteps)
@@ -197,15 +199,17 @@ class Device:
         self._check(lib.dcpgpu_trace_fetch(self._h, _ptr(off), _ptr(ids), _ptr(sz)))
         return alt, off, ids, sz
 
-    def trace_pairs(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False):
-        """Returns (alt_cost[n], paths) with paths[i] = (state_ids uint16[], seqsizes uint8[])."""
+    def trace_pairs(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False, keep_trellis=False):
+        """Returns (alt_cost[n], paths) with paths[i] = (state_ids uint16[], seqsizes uint8[]).
+        keep_trellis=True also materialises the whole trellis (see trace_trellis)."""
         pairs = np.ascontiguousarray(pairs)
         if pairs.dtype != PAIR_DTYPE:
             pairs = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 4).view(PAIR_DTYPE).reshape(-1)
         n = pairs.shape[0]
         alt = np.empty(n, dtype=np.float32)
         nsteps = np.zeros(n, dtype=np.int32)
-        self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs), flags_of(multi_hits, hmmer3_compat),
+        self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs),
+                                           flags_of(multi_hits, hmmer3_compat, keep_trellis),
                                            _ptr(alt), _ptr(nsteps)))
         off = np.zeros(n + 1, dtype=np.int64)
         off[1:] = np.cumsum(nsteps)

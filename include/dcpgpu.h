@@ -53,6 +53,9 @@ enum
 /* flags for score/trace: the two booleans of dcp_scan_setup (deciphon.h:11-13) */
 #define DCPGPU_MULTI_HITS 1u
 #define DCPGPU_HMMER3_COMPAT 2u
+/* trace_pairs only: materialise the whole bit-packed trellis (for dcpgpu_trace_trellis) instead
+ * of deciding just the words the path visits.  Paths are identical either way. */
+#define DCPGPU_KEEP_TRELLIS 4u
 
 typedef struct dcpgpu_ctx dcpgpu_ctx;
 
@@ -125,15 +128,17 @@ int64_t dcpgpu_last_redo(dcpgpu_ctx const *ctx);
 int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx);
 
 /* ---- trace pass: viterbi_path + trellis_unzip for the given (hit) pairs -----------------
- * Builds the reference's bit-packed trellis (trellis.h:12-56) on the device, walks it
- * back T@L -> S@0 on the device and reports the number of steps of every path. */
+ * Decides the reference's bit-packed trellis words (trellis.h:12-56) on the device -- only the
+ * words the path visits unless DCPGPU_KEEP_TRELLIS asks for all of them --, walks back
+ * T@L -> S@0 on the device and reports the number of steps of every path. */
 int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs, uint32_t flags,
                        float *alt_cost, int32_t *nsteps);
 /* Steps of all traced paths, path i at [offsets[i], offsets[i] + nsteps[i]) in path order
  * (S first): state ids as in state.h:7-25 and emitted nucleotides per step. */
 int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_ids,
                        uint8_t *seqsizes);
-/* Raw trellis words of traced pair i: xnodes[len+1], nodes[(len+1)*K] (tests, debugging). */
+/* Raw trellis words of traced pair i: xnodes[len+1], nodes[(len+1)*K] (tests, debugging).
+ * Needs DCPGPU_KEEP_TRELLIS in the flags of the preceding dcpgpu_trace_pairs. */
 int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t *nodes);
 
 /* Measured non-tensor FP32 issue rate of this GPU in tera lane-operations per second (the

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from deciphon_b200 import synth
-from deciphon_b200.device import PAIR_DTYPE
+from deciphon_b200.device import PAIR_DTYPE, DcpGpuError
 
 pytestmark = pytest.mark.gpu
 
@@ -135,17 +135,25 @@ def test_score_and_trace_synthetic_K(device, oracle, node_pool, K):
             if np.isfinite(lrt) and lrt >= 0:
                 hit_rows.append(rows[j])
         hit_rows = hit_rows[:4] + rows[-1:]  # also trace a non-hit: the trellis must still match
-        talt, paths = device.trace_pairs(_pairs(hit_rows), mh, h3)
+        # default route: only the trellis words the path visits are decided (trace_walk.cuh)
+        lalt, lpaths = device.trace_pairs(_pairs(hit_rows), mh, h3)
+        if K <= 2048:  # larger profiles run on the generic kernel, which always keeps its trellis
+            with pytest.raises(DcpGpuError):
+                device.trace_trellis(0, hit_rows[0][3], K)
+        # the whole bit matrix on request (trace_argmin.cuh), compared word for word
+        talt, paths = device.trace_pairs(_pairs(hit_rows), mh, h3, keep_trellis=True)
         for j, (_, ri, st, ln) in enumerate(hit_rows):
             x = np.ascontiguousarray(reads[ri][st:st + ln])
             xt = oracle.xtrans(ln, mh, h3)
             oalt, oxn, ond = oracle.trace(costs, xt, x)
             assert _bits(talt[j:j + 1])[0] == _bits(oalt.reshape(1))[0]
+            assert _bits(lalt[j:j + 1])[0] == _bits(oalt.reshape(1))[0]
             gxn, gnd = device.trace_trellis(j, ln, K)
             assert np.array_equal(gxn, oxn), (K, j, "xnodes")
             assert np.array_equal(gnd, ond), (K, j, "nodes")
             oids, osz = oracle.unzip(K, ln, oxn, ond)
             assert np.array_equal(paths[j][0], oids) and np.array_equal(paths[j][1], osz)
+            assert np.array_equal(lpaths[j][0], oids) and np.array_equal(lpaths[j][1], osz), (K, j, "lazy walk")
             assert int(paths[j][1].sum()) == ln
 
 
