@@ -106,6 +106,7 @@ struct dcpgpu_ctx
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
   bool forked = false;
   int side_next = 0;
+  cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
   bool timed = false;
   double last_cells = 0;
   int64_t launches = 0; // cumulative count of kernels this library launched
@@ -365,6 +366,7 @@ ReadsView reads_view(dcpgpu_ctx const *ctx);
 // stream the next class kernel goes to
 cudaStream_t launch_stream(dcpgpu_ctx *ctx)
 {
+  if (ctx->pinned) return ctx->pinned;
   if (!ctx->forked) return ctx->stream;
   cudaStream_t s = ctx->side[ctx->side_next];
   ctx->side_next = (ctx->side_next + 1) % dcpgpu_ctx::NSIDE;
@@ -1333,23 +1335,20 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     size_t const have = ctx->dump_cap * sizeof(float);
     size_t const budget = std::min<size_t>((fr + have) / 2, size_t(24) << 30) / sizeof(float);
     if ((rc = ensure(ctx, ctx->d_dump_off, ctx->dump_off_cap, n))) return rc;
-    std::vector<long long> dump_off(n, 0);
-    // class-major: every launch then holds many pairs of ONE kernel class (full occupancy)
+    // class-major: every launch then holds many pairs of ONE kernel class
     std::vector<std::vector<long long>> by_class(NCLASS);
     for (long long i : fast) by_class[(size_t)kernel_class(ctx, pairs[i].profile)].push_back(i);
-    // size the dump buffer ONCE (largest chunk any class will need): reallocating tens of GB
-    // between launches costs more than the kernels
+    // size the dump buffer ONCE (a full round, or the largest single pair): reallocating tens of
+    // GB between launches costs more than the kernels
     {
-      size_t need = 0;
-      for (int cls = 1; cls < NCLASS; ++cls)
+      size_t need = 0, all = 0;
+      for (long long i : fast)
       {
-        size_t tot_cls = 0;
-        for (long long i : by_class[(size_t)cls])
-          tot_cls += DumpView::floats(pairs[i].len, ctx->h_profiles[(size_t)pairs[i].profile].Kpad);
-        need = std::max(need, std::min(tot_cls, budget));
-        for (long long i : by_class[(size_t)cls])
-          need = std::max(need, DumpView::floats(pairs[i].len, ctx->h_profiles[(size_t)pairs[i].profile].Kpad));
+        size_t const f = DumpView::floats(pairs[i].len, ctx->h_profiles[(size_t)pairs[i].profile].Kpad);
+        need = std::max(need, f);
+        all += f;
       }
+      need = std::max(need, std::min(all, budget));
       if (need > ctx->dump_cap)
       {
         if (ctx->d_dump) CU(cudaFree(ctx->d_dump));
@@ -1359,52 +1358,75 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
         ctx->dump_cap = need;
       }
     }
+    // Rounds bounded by the dump budget; inside a round every kernel class present gets its own
+    // side stream (dump kernel, then the walk or argmin kernels behind it), so the low-occupancy
+    // launches of the large-profile classes overlap instead of adding up their tails.
+    std::vector<long long> sorted; // pairs of the fast route, largest kernel class first
+    for (int cls = NCLASS - 1; cls >= 1; --cls)
+      sorted.insert(sorted.end(), by_class[(size_t)cls].begin(), by_class[(size_t)cls].end());
+    auto cls_of = [&](long long i) { return kernel_class(ctx, pairs[i].profile); };
     auto run_fast = [&]() -> int {
-      for (int cls = NCLASS - 1; cls >= 1; --cls)
+      size_t c0 = 0;
+      while (c0 < sorted.size())
       {
-        std::vector<long long> const &list = by_class[(size_t)cls];
-        size_t c0 = 0;
-        while (c0 < list.size())
+        // round [c0, c1)
+        size_t c1 = c0, floats = 0;
+        std::vector<long long> doff;
+        while (c1 < sorted.size())
         {
-          // chunk [c0, c1) bounded by the dump budget
-          size_t c1 = c0, floats = 0;
-          while (c1 < list.size())
+          dcpgpu_pair const &pr = pairs[sorted[c1]];
+          size_t const f = DumpView::floats(pr.len, ctx->h_profiles[(size_t)pr.profile].Kpad);
+          if (c1 > c0 && floats + f > budget) break;
+          doff.push_back((long long)floats);
+          floats += f;
+          ++c1;
+        }
+        size_t const cn = c1 - c0;
+        if (floats > ctx->dump_cap) return fail(ctx, DCPGPU_ESTATE, "trace: dump buffer too small (internal error)");
+        // groups of one class: [g0, g1) relative to c0; tile prefix sums restart per group
+        std::vector<size_t> gstart;
+        std::vector<long long> tile_off;
+        std::vector<size_t> tstart;
+        for (size_t i = 0; i < cn; ++i)
+        {
+          if (i == 0 || cls_of(sorted[c0 + i]) != cls_of(sorted[c0 + i - 1]))
           {
-            dcpgpu_pair const &pr = pairs[list[c1]];
-            size_t const f = DumpView::floats(pr.len, ctx->h_profiles[(size_t)pr.profile].Kpad);
-            if (c1 > c0 && floats + f > budget) break;
-            dump_off[(size_t)list[c1]] = (long long)floats;
-            floats += f;
-            ++c1;
+            gstart.push_back(i);
+            tstart.push_back(tile_off.size());
+            tile_off.push_back(0);
           }
-          size_t const cn = c1 - c0;
-          if (floats > ctx->dump_cap) return fail(ctx, DCPGPU_ESTATE, "trace: dump buffer too small (internal error)");
-          std::vector<long long> tile_off(cn + 1, 0), doff(cn);
-          for (size_t i = 0; i < cn; ++i)
-          {
-            tile_off[i + 1] = tile_off[i] + (pairs[list[c0 + i]].len + ARGMIN_ROWS - 1) / ARGMIN_ROWS;
-            doff[i] = dump_off[(size_t)list[c0 + i]];
-          }
-          if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, cn))) return rc;
-          if ((rc = ensure(ctx, ctx->d_tile_off, ctx->tile_off_cap, cn + 1))) return rc;
-          CU(cudaMemcpyAsync(ctx->d_order, list.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-          CU(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), (cn + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-          // dump offsets are indexed by the item's position in this launch
-          CU(cudaMemcpyAsync(ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-          CU(cudaMemsetAsync(ctx->d_counters + cls, 0, sizeof(unsigned long long), ctx->stream));
+          tile_off.push_back(tile_off.back() + (pairs[sorted[c0 + i]].len + ARGMIN_ROWS - 1) / ARGMIN_ROWS);
+        }
+        gstart.push_back(cn);
+        if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, cn))) return rc;
+        if ((rc = ensure(ctx, ctx->d_tile_off, ctx->tile_off_cap, tile_off.size()))) return rc;
+        CU(cudaMemcpyAsync(ctx->d_order, sorted.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), tile_off.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        // dump offsets are indexed by the item's position in its launch
+        CU(cudaMemcpyAsync(ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_counters, 0, NCLASS * sizeof(unsigned long long), ctx->stream));
+        if ((rc = fork_streams(ctx))) return rc;
+        for (size_t gi = 0; gi + 1 < gstart.size(); ++gi)
+        {
+          size_t const g0 = gstart[gi], gn = gstart[gi + 1] - g0;
+          int const cls = cls_of(sorted[c0 + g0]);
+          cudaStream_t const st = ctx->side[gi % dcpgpu_ctx::NSIDE];
+          ctx->pinned = st; // the group's kernels depend on each other: one stream
           ScoreArgs sa{};
           sa.profiles = ctx->d_profiles;
           sa.reads = reads_view(ctx);
           sa.xt = ctx->d_xt[flags & 3u];
           sa.pairs = ctx->d_tpairs;
-          sa.order = ctx->d_order;
-          sa.nitems = cn;
+          sa.order = ctx->d_order + g0;
+          sa.nitems = gn;
           sa.counter = ctx->d_counters + cls;
           sa.out = ctx->d_tout;
           sa.nhits = ctx->d_counters + 27;
           sa.dump = ctx->d_dump;
-          sa.dump_off = ctx->d_dump_off;
-          if ((rc = launch_class_t<true>(ctx, cls, sa))) return rc;
+          sa.dump_off = ctx->d_dump_off + g0;
+          rc = launch_class_t<true>(ctx, cls, sa);
+          ctx->pinned = nullptr;
+          if (rc) return rc;
           if (!keep)
           { // paths only: walk the dumped values directly
             LazyWalkArgs z{};
@@ -1412,55 +1434,55 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
             z.reads = reads_view(ctx);
             z.xt = ctx->d_xt[flags & 3u];
             z.pairs = ctx->d_tpairs;
-            z.order = ctx->d_order;
-            z.nitems = (long long)cn;
+            z.order = ctx->d_order + g0;
+            z.nitems = (long long)gn;
             z.dump = ctx->d_dump;
-            z.dump_off = ctx->d_dump_off;
+            z.dump_off = ctx->d_dump_off + g0;
             z.nsteps = ctx->d_nsteps;
             z.slot_off = ctx->d_lz_off;
             z.overflow = ctx->d_counters + 22;
             z.ids = ctx->d_lz_ids;
             z.sizes = ctx->d_lz_sz;
-            lazy_walk_kernel<<<(unsigned)((cn + LAZY_WARPS - 1) / LAZY_WARPS), 32 * LAZY_WARPS, 0, ctx->stream>>>(z);
+            lazy_walk_kernel<<<(unsigned)((gn + LAZY_WARPS - 1) / LAZY_WARPS), 32 * LAZY_WARPS, 0, st>>>(z);
             CU(cudaGetLastError());
             ctx->launches += 1;
-            CU(cudaStreamSynchronize(ctx->stream));
-            c0 = c1;
             continue;
           }
+          long long const *toff = ctx->d_tile_off + tstart[gi];
           ArgminArgs g{};
           g.profiles = ctx->d_profiles;
           g.reads = reads_view(ctx);
           g.xt = ctx->d_xt[flags & 3u];
           g.pairs = ctx->d_tpairs;
-          g.order = ctx->d_order;
-          g.tile_off = ctx->d_tile_off;
-          g.nitems = (long long)cn;
+          g.order = ctx->d_order + g0;
+          g.tile_off = toff;
+          g.nitems = (long long)gn;
           g.dump = ctx->d_dump;
-          g.dump_off = ctx->d_dump_off;
+          g.dump_off = ctx->d_dump_off + g0;
           g.xnodes = ctx->d_xnodes;
           g.nodes = ctx->d_nodes;
           g.xnode_off = ctx->d_xnode_off;
           g.node_off = ctx->d_node_off;
-          trace_argmin_kernel<<<(unsigned)tile_off[cn], ARGMIN_THREADS, 0, ctx->stream>>>(g);
+          trace_argmin_kernel<<<(unsigned)tile_off[tstart[gi] + gn], ARGMIN_THREADS, 0, st>>>(g);
           CU(cudaGetLastError());
           WalkCountArgs w{};
           w.profiles = ctx->d_profiles;
           w.pairs = ctx->d_tpairs;
-          w.order = ctx->d_order;
-          w.nitems = (long long)cn;
+          w.order = ctx->d_order + g0;
+          w.nitems = (long long)gn;
           w.xnodes = ctx->d_xnodes;
           w.nodes = ctx->d_nodes;
           w.xnode_off = ctx->d_xnode_off;
           w.node_off = ctx->d_node_off;
           w.nsteps = ctx->d_nsteps;
-          walk_count_kernel<<<(unsigned)((cn + 63) / 64), 64, 0, ctx->stream>>>(w);
+          walk_count_kernel<<<(unsigned)((gn + 63) / 64), 64, 0, st>>>(w);
           CU(cudaGetLastError());
           ctx->launches += 2;
-          // host vectors and the device order/tile buffers are reused by the next chunk
-          CU(cudaStreamSynchronize(ctx->stream));
-          c0 = c1;
         }
+        if ((rc = join_streams(ctx))) return rc;
+        // host vectors and the device order/tile/offset buffers are reused by the next round
+        CU(cudaStreamSynchronize(ctx->stream));
+        c0 = c1;
       }
       return 0;
     };

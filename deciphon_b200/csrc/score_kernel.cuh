@@ -75,6 +75,9 @@ struct ScoreArgs
 // Layout of one traced pair's value dump: rows l = 1..L (row 0 is all +INF except B = SB).
 //   M, I, D : [L][Kpad] each, node k at column k (= vl*Q + q)
 //   xs      : [L][8] = N, B, J, E, C
+// Dumped DP values of one pair: M, I, D as [L][Kpad] with node k of a row at layout_pos(k)
+// (the order the lanes hold them, so a row is written with full-width stores), then
+// N, B, J, E, C of every row as [L][8].
 struct DumpView
 {
   float *M, *I, *D, *xs;
@@ -157,6 +160,19 @@ __device__ __forceinline__ void load_chunks(float (&e)[Q], float const *__restri
     e[N4 * 4 + 1] = v.y;
   }
   if constexpr ((Q & 1) != 0) e[Q - 1] = __ldg(row + VL * (Q - 1) + vl);
+}
+
+// The same layout, written: Q values of virtual lane vl into one row (full-width coalesced stores).
+template <int Q, int VL>
+__device__ __forceinline__ void store_chunks(float *row, int vl, float const (&v)[Q])
+{
+  constexpr int N4 = Q / 4;
+#pragma unroll
+  for (int c = 0; c < N4; ++c)
+    __stcs(reinterpret_cast<float4 *>(row + c * 4 * VL) + vl, make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]));
+  if constexpr ((Q & 2) != 0)
+    __stcs(reinterpret_cast<float2 *>(row + VL * (N4 * 4)) + vl, make_float2(v[N4 * 4], v[N4 * 4 + 1]));
+  if constexpr ((Q & 1) != 0) __stcs(row + VL * (Q - 1) + vl, v[Q - 1]);
 }
 
 // Per-lane base pointers into a profile's emission table: a code row is then reached with ONE
@@ -505,14 +521,10 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q
 
   if constexpr (DUMP)
   { // trace pass: the row's final values, for the argmin kernels
-    size_t const at = (size_t)(l - 1) * pd.Kpad + (size_t)vl * Q;
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      dv.M[at + q] = M[q];
-      dv.I[at + q] = I[q];
-      dv.D[at + q] = D[q];
-    }
+    size_t const at = (size_t)(l - 1) * pd.Kpad; // rows in the emission tables' lane-chunked order
+    store_chunks<Q, VL>(dv.M + at, vl, M);
+    store_chunks<Q, VL>(dv.I + at, vl, I);
+    store_chunks<Q, VL>(dv.D + at, vl, D);
     if (warp == 0)
     {
       float *xr = dv.xs + (size_t)(l - 1) * 8;

@@ -88,8 +88,9 @@ __global__ void __launch_bounds__(ARGMIN_THREADS, 2) trace_argmin_kernel(ArgminA
   }
   __syncthreads();
 
-  auto valM = [&](int l, int k) { return l >= 1 ? dv.M[(size_t)(l - 1) * Kpad + k] : INF; };
-  auto valD = [&](int l, int k) { return l >= 1 ? dv.D[(size_t)(l - 1) * Kpad + k] : INF; };
+  int const LQ = pd.Q, LVL = 32 * pd.W; // dumped rows are in layout_pos order
+  auto valM = [&](int l, int k) { return l >= 1 ? dv.M[(size_t)(l - 1) * Kpad + layout_pos(k, LQ, LVL)] : INF; };
+  auto valD = [&](int l, int k) { return l >= 1 ? dv.D[(size_t)(l - 1) * Kpad + layout_pos(k, LQ, LVL)] : INF; };
   auto valX = [&](int l, int j) { return dv.xs[(size_t)(l - 1) * 8 + j]; }; // l >= 1: N,B,J,E,C
 
   // per (row, t): background emission; per window row: B
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(ARGMIN_THREADS, 2) trace_argmin_kernel(ArgminA
   for (int k = threadIdx.x; k < K; k += ARGMIN_THREADS)
   {
     int const pk = layout_pos(k, pd.Q, 32 * pd.W);
+    int const pk1 = k > 0 ? layout_pos(k - 1, pd.Q, 32 * pd.W) : 0;
     float const bm = __ldg(pd.core + C_BM * Kpad + pk), mm = __ldg(pd.core + C_MM * Kpad + pk),
                 mi = __ldg(pd.core + C_MI * Kpad + pk), md = __ldg(pd.core + C_MD * Kpad + pk),
                 im = __ldg(pd.core + C_IM * Kpad + pk), ii = __ldg(pd.core + C_II * Kpad + pk),
@@ -121,12 +123,12 @@ __global__ void __launch_bounds__(ARGMIN_THREADS, 2) trace_argmin_kernel(ArgminA
     {
       int const lz = r0 - 5 + j;
       bool const ok = lz >= 1 && lz <= L;
-      size_t const at = ok ? (size_t)(lz - 1) * Kpad + k : 0;
-      wM[j] = ok ? dv.M[at] : INF;
-      wI[j] = ok ? dv.I[at] : INF;
-      wM1[j] = ok && k > 0 ? dv.M[at - 1] : INF;
-      wI1[j] = ok && k > 0 ? dv.I[at - 1] : INF;
-      wD1[j] = ok && k > 0 ? dv.D[at - 1] : INF;
+      size_t const row = ok ? (size_t)(lz - 1) * Kpad : 0;
+      wM[j] = ok ? dv.M[row + pk] : INF;
+      wI[j] = ok ? dv.I[row + pk] : INF;
+      wM1[j] = ok && k > 0 ? dv.M[row + pk1] : INF;
+      wI1[j] = ok && k > 0 ? dv.I[row + pk1] : INF;
+      wD1[j] = ok && k > 0 ? dv.D[row + pk1] : INF;
     }
 #pragma unroll
     for (int r = 0; r < ARGMIN_ROWS; ++r)

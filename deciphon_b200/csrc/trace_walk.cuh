@@ -102,8 +102,9 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
       size_t const row = (size_t)(l - 1) * Kpad;
       for (int k = lane; k < c.pd.K; k += 32)
       {
-        DCP_UPD(ev, c.dv.M[row + k], ei, 2 * k + 0);
-        DCP_UPD(ev, c.dv.D[row + k], ei, 2 * k + 1);
+        int const pos = layout_pos(k, c.pd.Q, 32 * c.pd.W);
+        DCP_UPD(ev, c.dv.M[row + pos], ei, 2 * k + 0);
+        DCP_UPD(ev, c.dv.D[row + pos], ei, 2 * k + 1);
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1)
@@ -183,6 +184,7 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
     int const k = (state & 0x3fff) - 1; // state_core_idx, state.c:25
     if (k < 0 || k >= c.pd.K) return false;
     int const pk = layout_pos(k, c.pd.Q, 32 * c.pd.W);
+    int const pk1 = k > 0 ? layout_pos(k - 1, c.pd.Q, 32 * c.pd.W) : 0; // node k-1 in a dumped row
     float const *core = c.pd.core;
     if (msb == ST_M)
     { // emission length 5..1; BM, MM, IM, DM  (viterbi.c:485-530)
@@ -194,7 +196,7 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
           sv = lz < 0 ? INF : lz == 0 ? xt[X_SB] : X(lz, 1);
         else if (k > 0 && lz >= 1)
         {
-          size_t const at = (size_t)(lz - 1) * Kpad + (k - 1);
+          size_t const at = (size_t)(lz - 1) * Kpad + pk1;
           sv = src == 1 ? c.dv.M[at] : src == 2 ? c.dv.I[at] : c.dv.D[at];
         }
         else
@@ -220,7 +222,7 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
         float sv = INF;
         if (lz >= 1)
         {
-          size_t const at = (size_t)(lz - 1) * Kpad + k;
+          size_t const at = (size_t)(lz - 1) * Kpad + pk;
           sv = w ? c.dv.M[at] : c.dv.I[at];
         }
         float const tr = __ldg(core + (size_t)(w ? C_MI : C_II) * Kpad + pk);
@@ -238,7 +240,7 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
       if (k <= 0) return false;
       if (lane < 2)
       {
-        size_t const at = (size_t)(l - 1) * Kpad + (k - 1);
+        size_t const at = (size_t)(l - 1) * Kpad + pk1;
         cand = lane == 0 ? c.dv.M[at] + __ldg(core + (size_t)C_MD * Kpad + pk)
                          : c.dv.D[at] + __ldg(core + (size_t)C_DD * Kpad + pk);
         tag = lane;
