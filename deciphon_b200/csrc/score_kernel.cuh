@@ -285,6 +285,13 @@ struct ScoreCfg
 {
   static constexpr int GROUPS = W == 1 ? 4 : 1; // independent pairs per CTA
   static constexpr int THREADS = 32 * W * GROUPS;
+  // CTAs per SM the register allocation is told to allow: stating the occupancy each class
+  // reaches anyway lets ptxas spend the registers up to that step on a better schedule
+  template <int Q>
+  static constexpr int min_blocks()
+  {
+    return W != 1 ? 1 : Q >= 6 ? 2 : Q >= 4 ? 3 : Q == 3 ? 4 : Q == 2 ? 5 : 6;
+  }
   // Long-code rows through the TMA ring?  Measured on B200 (profiles/): CTA-wide bulk copies
   // (W > 1, 2..8 KB each) beat per-lane loads, 1 KB per-warp copies (W = 1) do not.
   static constexpr bool TMA_RING = W > 1;
@@ -665,7 +672,7 @@ constexpr size_t score_smem_bytes()
 }
 
 template <int Q, int W, bool DUMP = false>
-__global__ void __launch_bounds__(ScoreCfg<W>::THREADS) score_reg_kernel(ScoreArgs a)
+__global__ void __launch_bounds__(ScoreCfg<W>::THREADS, ScoreCfg<W>::template min_blocks<Q>()) score_reg_kernel(ScoreArgs a)
 {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ Mail mail[2 * W];

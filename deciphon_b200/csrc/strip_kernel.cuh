@@ -189,8 +189,10 @@ __device__ __forceinline__ void strip_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip
     s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
 }
 
+// Occupancy beats registers for Q <= 6 (12 warps per SM at 168 registers, a few spilled values:
+// +12 % at Q = 6); Q = 7, 8 need the full 255 (measured, profiles/README.md).
 template <int Q, int W>
-__global__ void __launch_bounds__(32 * W) score_strip_kernel(StripArgs a)
+__global__ void __launch_bounds__(32 * W, Q <= 6 ? (12 / W > 0 ? 12 / W : 1) : 1) score_strip_kernel(StripArgs a)
 {
   constexpr int VL = 32 * W;
   __shared__ StripShared<W> sh;
