@@ -10,6 +10,7 @@
 #include "layout.cuh"
 #include "score_kernel.cuh"
 #include "strip_kernel.cuh"
+#include "sub_kernel.cuh"
 #include "trace_argmin.cuh"
 #include "trace_walk.cuh"
 
@@ -75,6 +76,7 @@ struct dcpgpu_ctx
 
   // reads
   uint32_t *d_words = nullptr;
+  long long nwords = 0;
   long long *d_seq_word = nullptr;
   int *d_seq_len = nullptr;
   std::vector<int> h_seq_len;
@@ -89,7 +91,7 @@ struct dcpgpu_ctx
   float2 *d_out = nullptr;
   size_t out_cap = 0;
   int64_t last_n = 0;
-  unsigned long long *d_counters = nullptr; // [16] work cursors + [16] = nhits
+  unsigned long long *d_counters = nullptr; // [NSLOTS]: class work cursors, then the SLOT_* counters
   int *d_class_profiles = nullptr;
   size_t class_profiles_cap = 0;
   Pair *d_pairs = nullptr;
@@ -107,6 +109,7 @@ struct dcpgpu_ctx
   bool forked = false;
   int side_next = 0;
   cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
+  bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
   bool timed = false;
   double last_cells = 0;
   int64_t launches = 0; // cumulative count of kernels this library launched
@@ -358,8 +361,21 @@ int sync_profiles(dcpgpu_ctx *ctx)
 }
 
 // Kernel classes: 0 = generic kernel; 1..8 = one warp per pair, Q nodes per lane;
-// 9..20 = W = 2/4/8 warps per pair, Q = 5..8.
-constexpr int NCLASS = 21;
+// 9..20 = W = 2/4/8 warps per pair, Q = 5..8; 21..32 = G = 2/4/8 pairs per warp (profiles of at
+// most 128/64/32 nodes on 16/8/4 lanes), Q = 5..8.
+constexpr int NCLASS = 33;
+// d_counters slots: work cursors of the classes first, then
+enum
+{
+  SLOT_OVERFLOW = 40,    // lazy walk: paths that outgrew their slot
+  SLOT_NREDO = 41,       // strip kernels: pairs to redo
+  SLOT_NHITS = 42,       // score pass: pairs with lrt >= 0
+  SLOT_FILL = 43,        // hits_fill cursor
+  SLOT_TRACE_CUR = 44,   // 4 cursors of the trellis-keeping trace kernels
+  SLOT_TRACE_NHITS = 48,
+  SLOT_BAD = 49,         // pack kernels: negative cost seen
+  NSLOTS = 64
+};
 
 ReadsView reads_view(dcpgpu_ctx const *ctx);
 
@@ -393,10 +409,19 @@ int join_streams(dcpgpu_ctx *ctx)
   return 0;
 }
 
+// classes in the order a pass launches them: generic, W = 8..2, one warp (Q = 8..1), sub-warp
+int launch_order(int i)
+{
+  if (i == 0) return 0;
+  if (i <= 20) return 21 - i;
+  return i;
+}
+
 int kernel_class(dcpgpu_ctx const *ctx, int profile)
 {
   ProfileDesc const &p = ctx->h_profiles[(size_t)profile];
   if (ctx->h_unsafe[(size_t)profile] || p.Q > MAXQ_REG) return 0;
+  if (p.VL < 32) return (p.VL == 16 ? 21 : p.VL == 8 ? 25 : 29) + (p.Q - 5);
   if (p.W == 1) return p.Q;
   if (p.Q < 5) return 0;
   if (p.W == 2) return 9 + (p.Q - 5);
@@ -427,11 +452,38 @@ int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
   return 0;
 }
 
+template <int Q, int G, bool DUMP>
+int launch_sub(dcpgpu_ctx *ctx, ScoreArgs const &a)
+{
+  constexpr int T = 32 * SUB_GROUPS;
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_sub_kernel<Q, G, DUMP>, T, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned long long const want = (a.nitems + G * SUB_GROUPS - 1) / (G * SUB_GROUPS);
+  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
+  score_sub_kernel<Q, G, DUMP><<<grid, T, 0, launch_stream(ctx)>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
 template <bool DUMP>
 int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 {
   switch (cls)
   {
+  case 21: return launch_sub<5, 2, DUMP>(ctx, a);
+  case 22: return launch_sub<6, 2, DUMP>(ctx, a);
+  case 23: return launch_sub<7, 2, DUMP>(ctx, a);
+  case 24: return launch_sub<8, 2, DUMP>(ctx, a);
+  case 25: return launch_sub<5, 4, DUMP>(ctx, a);
+  case 26: return launch_sub<6, 4, DUMP>(ctx, a);
+  case 27: return launch_sub<7, 4, DUMP>(ctx, a);
+  case 28: return launch_sub<8, 4, DUMP>(ctx, a);
+  case 29: return launch_sub<5, 8, DUMP>(ctx, a);
+  case 30: return launch_sub<6, 8, DUMP>(ctx, a);
+  case 31: return launch_sub<7, 8, DUMP>(ctx, a);
+  case 32: return launch_sub<8, 8, DUMP>(ctx, a);
   case 1: return launch_reg<1, 1, DUMP>(ctx, a);
   case 2: return launch_reg<2, 1, DUMP>(ctx, a);
   case 3: return launch_reg<3, 1, DUMP>(ctx, a);
@@ -501,7 +553,7 @@ template <class F>
 int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
 {
   unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, ctx->d_counters + 23, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&n, ctx->d_counters + SLOT_NREDO, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->last_redo = (int64_t)n;
   if (n == 0) return 0;
@@ -535,9 +587,9 @@ int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
   CU(cudaMemcpyAsync(ctx->d_redo_pairs, rp.data(), (size_t)n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_redo_order, order.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_redo_out, out_index.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters, 0, 23 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, NCLASS * sizeof(unsigned long long), ctx->stream));
   if ((rc = fork_streams(ctx))) return rc;
-  for (int c = 9; c < NCLASS; ++c)
+  for (int c = 9; c <= 20; ++c)
   {
     size_t const m = first[c + 1] - first[c];
     if (!m) continue;
@@ -551,7 +603,7 @@ int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
     a.nitems = m;
     a.counter = ctx->d_counters + c;
     a.out = ctx->d_out;
-    a.nhits = ctx->d_counters + 24;
+    a.nhits = ctx->d_counters + SLOT_NHITS;
     if ((rc = launch_class(ctx, c, a))) return rc;
   }
   if ((rc = join_streams(ctx))) return rc;
@@ -619,6 +671,7 @@ ReadsView reads_view(dcpgpu_ctx const *ctx)
   r.seq_word = ctx->d_seq_word;
   r.seq_len = ctx->d_seq_len;
   r.nseq = ctx->nseq;
+  r.nwords = ctx->nwords;
   return r;
 }
 
@@ -627,7 +680,7 @@ int begin_pass(dcpgpu_ctx *ctx, size_t npairs)
   int rc = sync_profiles(ctx);
   if (rc) return rc;
   if ((rc = ensure(ctx, ctx->d_out, ctx->out_cap, npairs))) return rc;
-  CU(cudaMemsetAsync(ctx->d_counters, 0, 26 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters, 0, NSLOTS * sizeof(unsigned long long), ctx->stream));
   ctx->forked = false;
   ctx->last_cells = 0;
   ctx->last_redo = 0;
@@ -714,6 +767,10 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   dcpgpu_ctx *ctx = new (std::nothrow) dcpgpu_ctx;
   if (!ctx) return DCPGPU_ENOMEM;
   ctx->device = device;
+  {
+    char const *v = std::getenv("DCPGPU_SUBWARP");
+    ctx->subwarp = !(v && v[0] == '0');
+  }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
@@ -725,7 +782,7 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_counters), 32 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_counters), NSLOTS * sizeof(unsigned long long));
   if (e != cudaSuccess)
   {
     delete ctx;
@@ -900,8 +957,9 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
 
   ProfileDesc d;
   d.K = K;
-  layout_shape(K, &d.Q, &d.W);
-  d.Kpad = 32 * d.W * d.Q;
+  layout_shape(K, &d.Q, &d.W, &d.VL, ctx->subwarp);
+  d.Kpad = d.VL * d.Q;
+  d.pad_ = 0;
   void *pem = nullptr, *pcore = nullptr, *pnb = nullptr;
   int rc;
   if ((rc = arena_alloc(ctx, (size_t)NCODES * d.Kpad * sizeof(float), &pem))) return rc;
@@ -924,9 +982,9 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   CU(cudaMemcpyAsync(ctx->d_stage + o_bg, bg_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 
   NodeRef const *drefs = reinterpret_cast<NodeRef const *>(ctx->d_stage + o_refs);
-  int const VL = 32 * d.W;
+  int const VL = d.VL;
   dim3 const grid((d.Kpad + 127) / 128, NCODES);
-  int *d_bad = reinterpret_cast<int *>(ctx->d_counters + 28);
+  int *d_bad = reinterpret_cast<int *>(ctx->d_counters + SLOT_BAD);
   CU(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
   pack_em_kernel<<<grid, 128, 0, ctx->stream>>>(drefs, K, d.Q, VL, d.Kpad, static_cast<float *>(pem), d_bad);
   pack_core_kernel<<<(d.Kpad + 127) / 128, 128, 0, ctx->stream>>>(
@@ -1003,6 +1061,7 @@ int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int6
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->h_seq_len.swap(seq_len);
   ctx->nseq = nseq;
+  ctx->nwords = (long long)words.size();
   ctx->maxlen = std::min(maxlen, DCPGPU_MAX_WINDOW);
   return 0;
 }
@@ -1068,7 +1127,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = fork_streams(ctx))) return rc;
   for (int ci = 0; ci < NCLASS; ++ci)
   {
-    int const c = ci ? NCLASS - ci : 0; // longest pairs first: their tail hides under the rest
+    int const c = launch_order(ci); // longest pairs first: their tail hides under the rest
     size_t const n = first[c + 1] - first[c];
     if (!n) continue;
     ScoreArgs a{};
@@ -1080,19 +1139,19 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     a.nitems = n;
     a.counter = ctx->d_counters + c;
     a.out = ctx->d_out;
-    a.nhits = ctx->d_counters + 24;
+    a.nhits = ctx->d_counters + SLOT_NHITS;
     if (c == 0)
     {
       GenArgs g{};
       g.s = a;
       if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
     }
-    else if (c >= 9)
+    else if (c >= 9 && c <= 20)
     { // speculative strips; failures are redone below
       StripArgs sa{};
       sa.s = a;
       sa.redo = ctx->d_redo;
-      sa.nredo = ctx->d_counters + 23;
+      sa.nredo = ctx->d_counters + SLOT_NREDO;
       if ((rc = launch_strip_class(ctx, c, sa))) return rc;
       any_strip = true;
     }
@@ -1153,7 +1212,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   if ((rc = ensure(ctx, ctx->d_class_profiles, ctx->class_profiles_cap, flat.size()))) return rc;
   {
     size_t strip_items = 0;
-    for (int c = 9; c < NCLASS; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
+    for (int c = 9; c <= 20; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
     if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, strip_items))) return rc;
   }
   bool any_strip = false;
@@ -1165,7 +1224,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   if ((rc = fork_streams(ctx))) return rc;
   for (int ci = 0; ci < NCLASS; ++ci)
   {
-    int const c = ci ? NCLASS - ci : 0;
+    int const c = launch_order(ci);
     size_t const n = first[c + 1] - first[c];
     if (!n) continue;
     ScoreArgs a{};
@@ -1179,19 +1238,19 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     a.nitems = (unsigned long long)n * (unsigned long long)nseq;
     a.counter = ctx->d_counters + c;
     a.out = ctx->d_out;
-    a.nhits = ctx->d_counters + 24;
+    a.nhits = ctx->d_counters + SLOT_NHITS;
     if (c == 0)
     {
       GenArgs g{};
       g.s = a;
       if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
     }
-    else if (c >= 9)
+    else if (c >= 9 && c <= 20)
     { // speculative strips; failures are redone below
       StripArgs sa{};
       sa.s = a;
       sa.redo = ctx->d_redo;
-      sa.nredo = ctx->d_counters + 23;
+      sa.nredo = ctx->d_counters + SLOT_NREDO;
       if ((rc = launch_strip_class(ctx, c, sa))) return rc;
       any_strip = true;
     }
@@ -1234,16 +1293,16 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
   if (!ctx || cap < 0 || !nhits) return fail(ctx, DCPGPU_EINVAL, "hits_fetch: bad argument");
   CU(cudaSetDevice(ctx->device));
   unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, ctx->d_counters + 24, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&n, ctx->d_counters + SLOT_NHITS, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *nhits = (int64_t)n;
   if (!hit_index || cap == 0 || n == 0) return 0;
   int rc_e = ensure(ctx, ctx->d_hit_idx, ctx->hit_idx_cap, (size_t)n);
   if (rc_e) return rc_e;
   long long *d_idx = ctx->d_hit_idx;
-  CU(cudaMemsetAsync(ctx->d_counters + 25, 0, sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + SLOT_FILL, 0, sizeof(unsigned long long), ctx->stream));
   long long const N = ctx->last_n;
-  hits_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, N, ctx->d_counters + 25,
+  hits_fill_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, N, ctx->d_counters + SLOT_FILL,
                                                                        (long long)n, d_idx);
   ctx->launches += 1;
   std::vector<long long> h((size_t)n);
@@ -1316,11 +1375,11 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     if ((rc = ensure(ctx, ctx->d_lz_sz, ctx->lz_sz_cap, (size_t)slot_off[n]))) return rc;
   }
   CU(cudaMemcpyAsync(ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters + 22, 0, sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + SLOT_OVERFLOW, 0, sizeof(unsigned long long), ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_counters + 26, 0, 6 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_counters + SLOT_TRACE_CUR, 0, 5 * sizeof(unsigned long long), ctx->stream));
 
   // ---- fast route: pairs whose profile runs on a register kernel -------------------------------
   // value dump by score_reg_kernel<Q,W,DUMP> + parallel argmin kernel (trace_argmin.cuh), in chunks
@@ -1421,7 +1480,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
           sa.nitems = gn;
           sa.counter = ctx->d_counters + cls;
           sa.out = ctx->d_tout;
-          sa.nhits = ctx->d_counters + 27;
+          sa.nhits = ctx->d_counters + SLOT_TRACE_NHITS;
           sa.dump = ctx->d_dump;
           sa.dump_off = ctx->d_dump_off + g0;
           rc = launch_class_t<true>(ctx, cls, sa);
@@ -1440,7 +1499,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
             z.dump_off = ctx->d_dump_off + g0;
             z.nsteps = ctx->d_nsteps;
             z.slot_off = ctx->d_lz_off;
-            z.overflow = ctx->d_counters + 22;
+            z.overflow = ctx->d_counters + SLOT_OVERFLOW;
             z.ids = ctx->d_lz_ids;
             z.sizes = ctx->d_lz_sz;
             lazy_walk_kernel<<<(unsigned)((gn + LAZY_WARPS - 1) / LAZY_WARPS), 32 * LAZY_WARPS, 0, st>>>(z);
@@ -1490,7 +1549,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     if (!keep)
     { // a path that outgrew its slot was only counted: give every pair its exact size and redo
       unsigned long long over = 0;
-      CU(cudaMemcpyAsync(&over, ctx->d_counters + 22, sizeof over, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(&over, ctx->d_counters + SLOT_OVERFLOW, sizeof over, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
       if (over)
       {
@@ -1504,7 +1563,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
         if ((rc = ensure(ctx, ctx->d_lz_ids, ctx->lz_ids_cap, (size_t)slot_off[n]))) return rc;
         if ((rc = ensure(ctx, ctx->d_lz_sz, ctx->lz_sz_cap, (size_t)slot_off[n]))) return rc;
         CU(cudaMemcpyAsync(ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemsetAsync(ctx->d_counters + 22, 0, sizeof(unsigned long long), ctx->stream));
+        CU(cudaMemsetAsync(ctx->d_counters + SLOT_OVERFLOW, 0, sizeof(unsigned long long), ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream)); // slot_off is re-read by nothing after this, but keep it simple
         if ((rc = run_fast())) return rc;
       }
@@ -1547,7 +1606,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
 
   // largest profiles first: they bound the duration of the pass
   size_t sc_off = 0;
-  static int const cursor_slot[4] = {26, 29, 30, 31};
+  static int const cursor_slot[4] = {SLOT_TRACE_CUR, SLOT_TRACE_CUR + 1, SLOT_TRACE_CUR + 2, SLOT_TRACE_CUR + 3};
   for (int c = 3; c >= 0; --c)
   {
     if (tb[c].empty()) continue;
@@ -1560,7 +1619,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     g.s.nitems = tb[c].size();
     g.s.counter = ctx->d_counters + cursor_slot[c];
     g.s.out = ctx->d_tout;
-    g.s.nhits = ctx->d_counters + 27;
+    g.s.nhits = ctx->d_counters + SLOT_TRACE_NHITS;
     g.xnodes = ctx->d_xnodes;
     g.nodes = ctx->d_nodes;
     g.xnode_off = ctx->d_xnode_off;

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(GEN_THREADS, 5) generic_kernel(GenArgs a)
     // row 0 (viterbi.c:472-474; before() writes all-zero trellis fields, :602-629)
     for (int k = lane; k < KG; k += 32)
     {
-      posk[k] = k < K ? layout_pos(k, pd.Q, 32 * pd.W) : 0;
+      posk[k] = k < K ? layout_pos(k, pd.Q, pd.VL) : 0;
       for (int sl = 0; sl < 6; ++sl)
       {
         rM[sl * (size_t)KG + k] = INF;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(32 * NW) trace_cta_kernel(GenArgs a)
     // row 0 (viterbi.c:472-474; before() writes all-zero trellis fields, :602-629)
     for (int k = threadIdx.x; k < KG; k += 32 * NW)
     {
-      posk[k] = k < K ? layout_pos(k, pd.Q, 32 * pd.W) : 0;
+      posk[k] = k < K ? layout_pos(k, pd.Q, pd.VL) : 0;
       for (int sl = 0; sl < 6; ++sl)
       {
         rM[sl * (size_t)KG + k] = INF;

@@ -28,9 +28,12 @@ struct ProfileDesc
   float const *core;
   float2 const *nulbg;
   int K;
-  int Q;
-  int W;
-  int Kpad; // 32 * W * Q
+  int Q;    // nodes per lane
+  int W;    // warps per pair
+  int Kpad; // VL * Q
+  int VL;   // virtual lanes a row is striped over: 32 * W, or 16/8/4 for profiles of at most
+            // 128/64/32 nodes (two/four/eight pairs share a warp, sub_kernel.cuh)
+  int pad_;
 };
 
 __host__ __device__ inline int layout_pos(int k, int Q, int VL)
@@ -44,11 +47,22 @@ __host__ __device__ inline int layout_pos(int k, int Q, int VL)
   return VL * q0 + vl * w + (q - q0);
 }
 
-inline void layout_shape(int K, int *Q, int *W)
+inline void layout_shape(int K, int *Q, int *W, int *VL, bool subwarp = true)
 {
+  if (subwarp && K <= 4 * MAXQ_REG * 4)
+  { // sub-warp: Q = 5..8 nodes on 4, 8 or 16 lanes (K <= 16 pads up to Q = 5 on 4 lanes)
+    int vl = K <= 4 * MAXQ_REG ? 4 : K <= 8 * MAXQ_REG ? 8 : 16;
+    int q = (K + vl - 1) / vl;
+    if (q < 5) q = 5;
+    *W = 1;
+    *VL = vl;
+    *Q = q;
+    return;
+  }
   int w = 1;
   while (32 * w * MAXQ_REG < K) w *= 2;
   *W = w;
+  *VL = 32 * w;
   *Q = (K + 32 * w - 1) / (32 * w);
 }
 
@@ -69,6 +83,7 @@ struct ReadsView
   long long const *seq_word; // [nseq] first word of each sequence
   int const *seq_len;        // [nseq]
   int nseq;
+  long long nwords;          // words in the buffer (sub_kernel.cuh clamps its read-ahead to it)
 };
 
 } // namespace dcp

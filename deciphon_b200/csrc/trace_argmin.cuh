@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(ARGMIN_THREADS, 2) trace_argmin_kernel(ArgminA
   }
   __syncthreads();
 
-  int const LQ = pd.Q, LVL = 32 * pd.W; // dumped rows are in layout_pos order
+  int const LQ = pd.Q, LVL = pd.VL; // dumped rows are in layout_pos order
   auto valM = [&](int l, int k) { return l >= 1 ? dv.M[(size_t)(l - 1) * Kpad + layout_pos(k, LQ, LVL)] : INF; };
   auto valD = [&](int l, int k) { return l >= 1 ? dv.D[(size_t)(l - 1) * Kpad + layout_pos(k, LQ, LVL)] : INF; };
   auto valX = [&](int l, int j) { return dv.xs[(size_t)(l - 1) * 8 + j]; }; // l >= 1: N,B,J,E,C
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(ARGMIN_THREADS, 2) trace_argmin_kernel(ArgminA
   //      dumped values of the five previous rows through registers (each value loaded once) ----
   for (int k = threadIdx.x; k < K; k += ARGMIN_THREADS)
   {
-    int const pk = layout_pos(k, pd.Q, 32 * pd.W);
-    int const pk1 = k > 0 ? layout_pos(k - 1, pd.Q, 32 * pd.W) : 0;
+    int const pk = layout_pos(k, pd.Q, pd.VL);
+    int const pk1 = k > 0 ? layout_pos(k - 1, pd.Q, pd.VL) : 0;
     float const bm = __ldg(pd.core + C_BM * Kpad + pk), mm = __ldg(pd.core + C_MM * Kpad + pk),
                 mi = __ldg(pd.core + C_MI * Kpad + pk), md = __ldg(pd.core + C_MD * Kpad + pk),
                 im = __ldg(pd.core + C_IM * Kpad + pk), ii = __ldg(pd.core + C_II * Kpad + pk),

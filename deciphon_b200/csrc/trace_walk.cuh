@@ -102,7 +102,7 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
       size_t const row = (size_t)(l - 1) * Kpad;
       for (int k = lane; k < c.pd.K; k += 32)
       {
-        int const pos = layout_pos(k, c.pd.Q, 32 * c.pd.W);
+        int const pos = layout_pos(k, c.pd.Q, c.pd.VL);
         DCP_UPD(ev, c.dv.M[row + pos], ei, 2 * k + 0);
         DCP_UPD(ev, c.dv.D[row + pos], ei, 2 * k + 1);
       }
@@ -183,8 +183,8 @@ __device__ __forceinline__ bool lazy_step(LazyCtx const &c, int &state, int &sta
   {
     int const k = (state & 0x3fff) - 1; // state_core_idx, state.c:25
     if (k < 0 || k >= c.pd.K) return false;
-    int const pk = layout_pos(k, c.pd.Q, 32 * c.pd.W);
-    int const pk1 = k > 0 ? layout_pos(k - 1, c.pd.Q, 32 * c.pd.W) : 0; // node k-1 in a dumped row
+    int const pk = layout_pos(k, c.pd.Q, c.pd.VL);
+    int const pk1 = k > 0 ? layout_pos(k - 1, c.pd.Q, c.pd.VL) : 0; // node k-1 in a dumped row
     float const *core = c.pd.core;
     if (msb == ST_M)
     { // emission length 5..1; BM, MM, IM, DM  (viterbi.c:485-530)

@@ -9,11 +9,15 @@ from deciphon_b200.device import Device, PAIR_DTYPE
 
 
 def shape(K):
+    """(W, Q, G) as csrc/layout.cuh layout_shape assigns them."""
+    if os.environ.get("DCPGPU_SUBWARP", "1") != "0" and K <= 128:
+        vl = 4 if K <= 32 else 8 if K <= 64 else 16
+        return 1, max(5, -(-K // vl)), 32 // vl
     W = 1
     while 32 * W * 8 < K:
         W *= 2
     Q = -(-K // (32 * W))
-    return W, Q
+    return W, Q, 1
 
 
 def main():
@@ -36,9 +40,9 @@ def main():
     whole = dev.last_kernel_ms()
     tot = 0.0
     rows = []
-    for W in (1, 2, 4, 8, 16):
+    for W, G in ((1, 8), (1, 4), (1, 2), (1, 1), (2, 1), (4, 1), (8, 1), (16, 1)):
         for Q in range(1, 9):
-            sel = np.nonzero((WQ[:, 0] == W) & (WQ[:, 1] == Q))[0]
+            sel = np.nonzero((WQ[:, 0] == W) & (WQ[:, 1] == Q) & (WQ[:, 2] == G))[0]
             if W == 16:
                 sel = np.nonzero(WQ[:, 0] >= 16)[0]
                 if Q > 1:
@@ -53,10 +57,10 @@ def main():
             dev.score_pairs(pr, multi_hits=True)
             ms = dev.last_kernel_ms()
             cells = float((sizes[pr["profile"]].astype(np.float64) * pr["len"]).sum())
-            rows.append((W, Q, len(sel), cells, ms, dev.last_redo()))
+            rows.append((W, Q, G, len(sel), cells, ms, dev.last_redo()))
             tot += ms
-    for W, Q, n, cells, ms, redo in rows:
-        print(f"W={W:2d} Q={Q} profiles={n:6d} cells={cells:.3e} ms={ms:8.2f} share={ms/tot:6.1%} GCUPS={cells/ms/1e6:7.1f} redo={redo}")
+    for W, Q, G, n, cells, ms, redo in rows:
+        print(f"W={W:2d} G={G} Q={Q} profiles={n:6d} cells={cells:.3e} ms={ms:8.2f} share={ms/tot:6.1%} GCUPS={cells/ms/1e6:7.1f} redo={redo}")
     print(f"sum of classes {tot:.1f} ms; whole grid pass {whole:.1f} ms")
     dev.close()
 
