@@ -347,7 +347,7 @@ def run_b200(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32-alu (non-tensor add/min issue; not hbm, not tensor)", "achieved": achieved,
                          "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "score_reg_kernel<Q> / generic_kernel<false> (score pass), rank 0",
+                         "kernel": "score pass = score_sub_kernel<Q,G> (K<=128) + score_reg_kernel<Q,1> (K<=256) + score_strip_kernel<Q,W> (K<=2048, exact redo of failed speculation) + generic_kernel<false> (rest), rank 0",
                          "ops_per_cell": OPS_PER_CELL, "kernel_gcups": stats["cells"] / (stats["score_ms"] * 1e-3) / 1e9,
                          "kernel_ms_per_step": stats["score_ms"] / args.steps, "peak_source": peak_src,
                          "hbm_gbs_measured": _measured_peaks().get("hbm_gbs")},
