@@ -109,6 +109,9 @@ struct dcpgpu_ctx
   bool forked = false;
   int side_next = 0;
   cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
+  Mail *d_col = nullptr; // boundary columns of the one-strip-per-launch kernels
+  size_t col_cap = 0;
+  bool strip_concurrent = false; // DCPGPU_STRIP=concurrent: the CTA-per-pair strip kernels (A/B switch)
   bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
   bool timed = false;
   double last_cells = 0;
@@ -539,11 +542,95 @@ int strip_dispatch(dcpgpu_ctx *ctx, int cls, F &&f)
 #undef DCP_SC
 }
 
+template <int Q, int W, bool FIRST, bool LAST>
+int launch_lstrip_one(dcpgpu_ctx *ctx, StripArgs const &a, unsigned long long count, cudaStream_t st)
+{
+  int per_sm = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_lstrip_kernel<Q, W, FIRST, LAST>, 32 * LSTRIP_WARPS, 0));
+  if (per_sm < 1) per_sm = 1;
+  unsigned long long const want = (count + LSTRIP_WARPS - 1) / LSTRIP_WARPS;
+  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
+  CU(cudaMemsetAsync(a.s.counter, 0, sizeof(unsigned long long), st));
+  score_lstrip_kernel<Q, W, FIRST, LAST><<<grid, 32 * LSTRIP_WARPS, 0, st>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+// Strips 0..W-1 of the items [item0, item0 + count) of one class, one launch each, in stream order.
+template <int Q, int W>
+int launch_lstrips(dcpgpu_ctx *ctx, StripArgs a, unsigned long long item0, unsigned long long count, cudaStream_t st)
+{
+  a.item0 = item0;
+  a.s.nitems = item0 + count;
+  int rc;
+  for (int w = 0; w < W; ++w)
+  {
+    a.strip = w;
+    if (w == 0) rc = launch_lstrip_one<Q, W, true, false>(ctx, a, count, st);
+    else if (w == W - 1) rc = launch_lstrip_one<Q, W, false, true>(ctx, a, count, st);
+    else rc = launch_lstrip_one<Q, W, false, false>(ctx, a, count, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// Boundary-column memory of a pass: `count[c]` items per strip class, windows up to maxlen.
+// If everything fits the budget every class gets its own region and the classes run
+// concurrently; otherwise the classes take turns with the whole buffer, in chunks.
+struct StripPlan
+{
+  size_t stride = 0;          // Mails per item
+  size_t region[NCLASS] = {}; // first Mail of the class's region
+  size_t chunk = 0;           // items per chunk when the classes take turns (0: all at once)
+};
+
+int plan_strips(dcpgpu_ctx *ctx, unsigned long long const *count, int maxlen, StripPlan *plan)
+{
+  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
+  size_t total = 0;
+  for (int c = 9; c <= 20; ++c)
+  {
+    plan->region[c] = total * plan->stride;
+    total += (size_t)count[c];
+  }
+  if (ctx->strip_concurrent || !total) return 0;
+  size_t fr = 0, tot = 0;
+  CU(cudaMemGetInfo(&fr, &tot));
+  size_t const have = ctx->col_cap * sizeof(Mail);
+  size_t const budget = std::min<size_t>((fr + have) / 2, size_t(16) << 30) / (plan->stride * sizeof(Mail));
+  size_t items = total;
+  if (total > budget)
+  {
+    plan->chunk = items = std::max<size_t>(budget, 1);
+    for (int c = 9; c <= 20; ++c) plan->region[c] = 0;
+  }
+  if (items * plan->stride <= ctx->col_cap) return 0;
+  if (ctx->d_col) CU(cudaFree(ctx->d_col));
+  ctx->d_col = nullptr;
+  ctx->col_cap = 0;
+  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_col), items * plan->stride * sizeof(Mail)));
+  ctx->col_cap = items * plan->stride;
+  return 0;
+}
+
 // classes 9..20: speculative strips first, the exact multi-warp kernel for the pairs that fail
-int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs const &a)
+int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs a, StripPlan const &plan)
 {
   return strip_dispatch(ctx, cls, [&](auto q, auto w) {
-    return launch_strip<decltype(q)::value, decltype(w)::value>(ctx, a);
+    constexpr int Q = decltype(q)::value, W = decltype(w)::value;
+    if (ctx->strip_concurrent) return launch_strip<Q, W>(ctx, a);
+    a.col = ctx->d_col + plan.region[cls];
+    a.col_stride = plan.stride;
+    unsigned long long const n = a.s.nitems;
+    if (!plan.chunk) return launch_lstrips<Q, W>(ctx, a, 0, n, launch_stream(ctx));
+    // the classes share one buffer: everything on the main stream, chunk after chunk
+    for (unsigned long long i0 = 0; i0 < n; i0 += plan.chunk)
+    {
+      int const rc = launch_lstrips<Q, W>(ctx, a, i0, std::min<unsigned long long>(plan.chunk, n - i0), ctx->stream);
+      if (rc) return rc;
+    }
+    return 0;
   });
 }
 
@@ -770,6 +857,8 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   {
     char const *v = std::getenv("DCPGPU_SUBWARP");
     ctx->subwarp = !(v && v[0] == '0');
+    v = std::getenv("DCPGPU_STRIP");
+    ctx->strip_concurrent = v && std::strcmp(v, "concurrent") == 0;
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -826,6 +915,7 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_dump);
   cudaFree(ctx->d_hit_idx);
   cudaFree(ctx->d_redo);
+  cudaFree(ctx->d_col);
   cudaFree(ctx->d_redo_pairs);
   cudaFree(ctx->d_redo_order);
   cudaFree(ctx->d_redo_out);
@@ -1120,6 +1210,12 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
+  StripPlan plan;
+  {
+    unsigned long long count[NCLASS];
+    for (int c = 0; c < NCLASS; ++c) count[c] = first[c + 1] - first[c];
+    if ((rc = plan_strips(ctx, count, maxlen, &plan))) return rc;
+  }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -1152,7 +1248,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       sa.s = a;
       sa.redo = ctx->d_redo;
       sa.nredo = ctx->d_counters + SLOT_NREDO;
-      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
+      if ((rc = launch_strip_class(ctx, c, sa, plan))) return rc;
       any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
@@ -1215,6 +1311,12 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     for (int c = 9; c <= 20; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
     if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, strip_items))) return rc;
   }
+  StripPlan plan;
+  {
+    unsigned long long count[NCLASS];
+    for (int c = 0; c < NCLASS; ++c) count[c] = (unsigned long long)(first[c + 1] - first[c]) * (unsigned long long)nseq;
+    if ((rc = plan_strips(ctx, count, ctx->maxlen, &plan))) return rc;
+  }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
@@ -1251,7 +1353,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       sa.s = a;
       sa.redo = ctx->d_redo;
       sa.nredo = ctx->d_counters + SLOT_NREDO;
-      if ((rc = launch_strip_class(ctx, c, sa))) return rc;
+      if ((rc = launch_strip_class(ctx, c, sa, plan))) return rc;
       any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
