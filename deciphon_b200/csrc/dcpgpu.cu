@@ -111,7 +111,6 @@ struct dcpgpu_ctx
   cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
   Mail *d_col = nullptr; // boundary columns of the one-strip-per-launch kernels
   size_t col_cap = 0;
-  bool strip_concurrent = false; // DCPGPU_STRIP=concurrent: the CTA-per-pair strip kernels (A/B switch)
   bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
   bool timed = false;
   double last_cells = 0;
@@ -513,19 +512,6 @@ int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 
 int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a) { return launch_class_t<false>(ctx, cls, a); }
 
-template <int Q, int W>
-int launch_strip(dcpgpu_ctx *ctx, StripArgs const &a)
-{
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_strip_kernel<Q, W>, 32 * W, 0));
-  if (per_sm < 1) per_sm = 1;
-  unsigned const grid = (unsigned)std::min<unsigned long long>(a.s.nitems, (unsigned long long)per_sm * ctx->sm_count);
-  score_strip_kernel<Q, W><<<grid, 32 * W, 0, launch_stream(ctx)>>>(a);
-  CU(cudaGetLastError());
-  ctx->launches += 1;
-  return 0;
-}
-
 // f(Q, W) for a strip class 9..20 (W = 2/4/8 x Q = 5..8)
 template <class F>
 int strip_dispatch(dcpgpu_ctx *ctx, int cls, F &&f)
@@ -569,7 +555,8 @@ int launch_lstrips(dcpgpu_ctx *ctx, StripArgs a, unsigned long long item0, unsig
     a.strip = w;
     if (w == 0) rc = launch_lstrip_one<Q, W, true, false>(ctx, a, count, st);
     else if (w == W - 1) rc = launch_lstrip_one<Q, W, false, true>(ctx, a, count, st);
-    else rc = launch_lstrip_one<Q, W, false, false>(ctx, a, count, st);
+    else if constexpr (W > 2) rc = launch_lstrip_one<Q, W, false, false>(ctx, a, count, st);
+    else rc = DCPGPU_ESTATE;
     if (rc) return rc;
   }
   return 0;
@@ -594,7 +581,7 @@ int plan_strips(dcpgpu_ctx *ctx, unsigned long long const *count, int maxlen, St
     plan->region[c] = total * plan->stride;
     total += (size_t)count[c];
   }
-  if (ctx->strip_concurrent || !total) return 0;
+  if (!total) return 0;
   size_t fr = 0, tot = 0;
   CU(cudaMemGetInfo(&fr, &tot));
   size_t const have = ctx->col_cap * sizeof(Mail);
@@ -619,7 +606,6 @@ int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs a, StripPlan const &p
 {
   return strip_dispatch(ctx, cls, [&](auto q, auto w) {
     constexpr int Q = decltype(q)::value, W = decltype(w)::value;
-    if (ctx->strip_concurrent) return launch_strip<Q, W>(ctx, a);
     a.col = ctx->d_col + plan.region[cls];
     a.col_stride = plan.stride;
     unsigned long long const n = a.s.nitems;
@@ -857,8 +843,6 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   {
     char const *v = std::getenv("DCPGPU_SUBWARP");
     ctx->subwarp = !(v && v[0] == '0');
-    v = std::getenv("DCPGPU_STRIP");
-    ctx->strip_concurrent = v && std::strcmp(v, "concurrent") == 0;
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

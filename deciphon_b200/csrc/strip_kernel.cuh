@@ -7,31 +7,27 @@
 // random (read, profile) pairs have B(l) == N(l)+NB on every row, median margin 4 nats), and N(l)
 // depends on the read alone.
 //
-// So each of the W warps of a CTA takes one STRIP of 32*Q nodes and runs the whole window with
-// the single-warp software-pipelined row, ASSUMING B(l) = N(l)+NB.  The only coupling left is
-// one-directional: strip w needs M, I, D (final) of the last node of strip w-1 for the same row,
-// which flows through a small shared-memory ring with producer/consumer row counters -- warps
-// run skewed by a row or two, no CTA barrier, no second delete-chain round.  The running
-// minimum of E travels with the boundary, so the LAST strip sees the true E(l): it carries the
-// J and C states and checks, row by row, that the assumption held.  If it did (bit-for-bit, the
-// minimum is the same float), every value computed is the exact one and alt = T(L) is written;
-// otherwise the pair is queued for the exact multi-warp kernel.  Results are therefore always
-// bit-identical to the reference -- speculation only decides which kernel produces them.
+// So a profile is cut into W STRIPS of 32*Q nodes and every strip runs the whole window with the
+// single-warp software-pipelined row, ASSUMING B(l) = N(l)+NB.  The only coupling left is
+// one-directional: strip w needs M, I, D (final) of the last node of strip w-1 for the same row.
+// Strip w of every pair of a kernel class is ONE LAUNCH and strip w+1 the next one on the same
+// stream; a warp runs one strip of one pair and the boundary {M, I, D, running min of E} of
+// every row travels through a per-pair column in global memory (16 bytes a row, fetched one row
+// ahead, overwritten in place).  The running minimum of E travels with it, so the LAST strip
+// sees the true E(l): it carries the J and C states and checks, row by row, that the assumption
+// held.  If it did (bit-for-bit, the minimum is the same float), every value computed is the
+// exact one and alt = T(L) is written; otherwise the pair is queued for the exact multi-warp
+// kernel.  Results are therefore always bit-identical to the reference -- speculation only
+// decides which kernel produces them.
+//
+// Measured alternatives (profiles/README.md): the W strips of a pair as the W warps of one CTA,
+// coupled through a shared-memory ring with producer/consumer row counters (15-25 % slower:
+// polling and reconvergence instructions, two strips' short-code rows competing for L1), and one
+// warp walking the strips of a pair inside one kernel (register-capped schedule).
 #pragma once
 #include "score_kernel.cuh"
 
 namespace dcp {
-
-constexpr int STRIP_RING = 8; // boundary slots per strip (rows a producer may run ahead)
-
-template <int W>
-struct StripShared
-{
-  Mail ring[W][STRIP_RING]; // {M, I, D of the strip's last node, running E} per row
-  int volatile prod[W];     // rows published by strip w
-  int volatile cons[W];     // rows of strip w consumed by strip w+1
-  unsigned long long next_item;
-};
 
 struct StripArgs
 {
@@ -44,11 +40,6 @@ struct StripArgs
   int strip;                     // which strip of the pair this launch runs
   unsigned long long item0;      // first item of this launch's range ([item0, s.nitems))
 };
-
-__device__ __forceinline__ void wait_ge(int volatile *p, int v)
-{
-  while (*p < v) __nanosleep(20); // back off: the producer may share this warp's scheduler
-}
 
 // d_lazy with a fixed incoming value for the head lane (the previous strip's final D)
 template <int Q>
@@ -67,289 +58,10 @@ __device__ __forceinline__ float d_lazy_in(Lane<Q> const &s, float (&D)[Q], bool
   return din;
 }
 
-template <int Q, int W, int J>
-__device__ __forceinline__ void strip_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q], float &xp, ProfileDesc const &pd,
-                                          unsigned hist, unsigned hist1, int lane, int warp, float NB, float EB,
-                                          float JB, StripShared<W> *sh, int l, float &E, float &x, bool &ok)
-{
-  constexpr int VL = 32 * W;
-  constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
-  int const vl = warp * 32 + lane;
-  uint32_t const rowb = (uint32_t)pd.Kpad * 4u;
-  RowBase<Q, VL> const rb(pd.em, vl);
-
-  // (A) finish row l with the one-nucleotide term (needs P(l-1), Q(l-1))
-  float M[Q], I[Q];
-  float xacc;
-  {
-    int const c1 = hist & 3;
-    float2 const nb = ldg_nulbg(pd.nulbg, c1);
-    float e[Q];
-    rb.load(e, (uint32_t)c1 * rowb);
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      M[q] = fminf(Mp[q], s.P[s1][q] + e[q]);
-      I[q] = fminf(Ip[q], s.Qv[s1][q] + nb.y);
-    }
-    xacc = fminf(xp, s.px[s1] + nb.x);
-  }
-
-  // emission rows of row l+1 for t = 2..5
-  int const c2 = 4 + (hist1 & 15), c3 = 20 + (hist1 & 63), c4 = 84 + (hist1 & 255), c5 = 340 + (hist1 & 1023);
-  float2 const nb2 = ldg_nulbg(pd.nulbg, c2), nb3 = ldg_nulbg(pd.nulbg, c3), nb4 = ldg_nulbg(pd.nulbg, c4),
-               nb5 = ldg_nulbg(pd.nulbg, c5);
-  float e2[Q], e3[Q], e4[Q], e5[Q];
-  rb.load(e2, (uint32_t)c2 * rowb);
-  rb.load(e3, (uint32_t)c3 * rowb);
-  rb.load(e4, (uint32_t)c4 * rowb);
-  rb.load(e5, (uint32_t)c5 * rowb);
-
-  // boundary of row l from the previous strip (final values; +INF for the first strip)
-  float bM = CUDART_INF_F, bI = CUDART_INF_F, bD = CUDART_INF_F, bE = CUDART_INF_F;
-  if (warp > 0)
-  {
-    wait_ge(&sh->prod[warp - 1], l);
-    __threadfence_block();
-    Mail const b = sh->ring[warp - 1][l & (STRIP_RING - 1)];
-    bM = b.M;
-    bI = b.I;
-    bD = b.D;
-    bE = b.E;
-    __syncwarp();
-    if (lane == 0) sh->cons[warp - 1] = l;
-  }
-  bool const head = lane == 0 && warp > 0;
-
-  // delete chain of row l (viterbi.c:538, 552-580); the head lane's predecessor is the boundary
-  float mprev = __shfl_up_sync(FULL_MASK, M[Q - 1], 1);
-  float iprev = __shfl_up_sync(FULL_MASK, I[Q - 1], 1);
-  if (head)
-  {
-    mprev = bM;
-    iprev = bI;
-  }
-  float D[Q];
-  D[0] = mprev + s.MD[0];
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    D[q] = M[q - 1] + s.MD[q];
-  {
-    float din0 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
-    if (head) din0 = bD;
-    D[0] = fminf(D[0], din0 + s.DD[0]);
-    d_sweep<Q>(s, D);
-  }
-
-  // row l+1, t = 2..5 (rows l-1..l-4 = ring slots s1..s4), in the shadow of the sweeps
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-  {
-    Mp[q] = fminf(min3(s.P[s1][q] + e2[q], s.P[s2][q] + e3[q], s.P[s3][q] + e4[q]), s.P[s4][q] + e5[q]);
-    Ip[q] = fminf(min3(s.Qv[s1][q] + nb2.y, s.Qv[s2][q] + nb3.y, s.Qv[s3][q] + nb4.y), s.Qv[s4][q] + nb5.y);
-  }
-  xp = fminf(min3(s.px[s1] + nb2.x, s.px[s2] + nb3.x, s.px[s3] + nb4.x), s.px[s4] + nb5.x);
-
-  {
-    float din1 = __shfl_up_sync(FULL_MASK, D[Q - 1], 1);
-    if (head) din1 = bD;
-    D[0] = fminf(D[0], din1 + s.DD[0]);
-    d_sweep<Q>(s, D);
-  }
-  float dprev = d_lazy_in<Q>(s, D, head, bD);
-
-  // running E over strips 0..warp; the last strip holds E(l) of the whole row
-  float const e = fminf(e_partial<Q>(M, D), bE);
-  if (warp < W - 1)
-  { // hand the boundary of row l to the next strip
-    wait_ge(&sh->cons[warp], l - STRIP_RING);
-    if (lane == 31) sh->ring[warp][l & (STRIP_RING - 1)] = Mail{M[Q - 1], I[Q - 1], D[Q - 1], e};
-    __threadfence_block();
-    __syncwarp();
-    if (lane == 31) sh->prod[warp] = l;
-  }
-  E = e;
-
-  // special states.  Lane 0: N, lane 3: R everywhere; lanes 1, 2 (J, C) only mean something in the
-  // last strip, which also verifies the speculated B.
-  x = xacc;
-  float const N = __shfl_sync(FULL_MASK, x, 0);
-  float const B = N + NB;
-  if (warp == W - 1)
-  {
-    float const Jv = __shfl_sync(FULL_MASK, x, 1);
-    float const Btrue = min3(B, e + EB, Jv + JB); // viterbi.c:495-496,582-583
-    ok = ok && (Btrue == B);
-    s.px[J] = fminf(e + s.xa, x + s.xb);
-  }
-  else
-    s.px[J] = x + s.xb;
-
-  s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    s.P[J][q] = fminf(min3(B + s.BM[q], M[q - 1] + s.MM[q], I[q - 1] + s.IM[q]), D[q - 1] + s.DM[q]);
-#pragma unroll
-  for (int q = 0; q < Q; ++q)
-    s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);
-}
-
-// Occupancy beats registers for Q <= 6 (12 warps per SM at 168 registers, a few spilled values:
-// +12 % at Q = 6); Q = 7, 8 need the full 255 (measured, profiles/README.md).
-template <int Q, int W>
-__global__ void __launch_bounds__(32 * W, Q <= 6 ? (12 / W > 0 ? 12 / W : 1) : 1) score_strip_kernel(StripArgs a)
-{
-  constexpr int VL = 32 * W;
-  __shared__ StripShared<W> sh;
-  int const lane = threadIdx.x & 31;
-  int const warp = threadIdx.x >> 5;
-
-  for (;;)
-  {
-    if (threadIdx.x == 0)
-    {
-      sh.next_item = atomicAdd(a.s.counter, 1ULL);
-      for (int w = 0; w < W; ++w)
-      {
-        sh.prod[w] = 0;
-        sh.cons[w] = 0;
-      }
-    }
-    __syncthreads();
-    unsigned long long const item = sh.next_item;
-    if (item >= a.s.nitems) break;
-
-    int p, sq, start, L;
-    long long oidx;
-    if (a.s.pairs)
-    {
-      oidx = a.s.order[item];
-      Pair const pr = a.s.pairs[oidx];
-      p = pr.profile; sq = pr.seq; start = pr.start; L = pr.len;
-    }
-    else
-    {
-      int const pi = (int)(item / (unsigned)a.s.nseq);
-      int const si = (int)(item - (unsigned long long)pi * (unsigned)a.s.nseq);
-      p = a.s.class_profiles[pi];
-      sq = a.s.seq0 + si;
-      start = 0;
-      oidx = (long long)(p - a.s.prof0) * a.s.nseq + si;
-      L = -1;
-    }
-    ProfileDesc const pd = a.s.profiles[p];
-    if (L < 0) L = min(min(pd.K * 50, 100000), a.s.reads.seq_len[sq]);
-    float const *xt = a.s.xt + (size_t)L * X_STRIDE;
-
-    Lane<Q> s;
-    int const Kpad = pd.Kpad;
-    int const vl = warp * 32 + lane;
-    load_chunks<Q, VL>(s.BM, pd.core + C_BM * Kpad, vl);
-    load_chunks<Q, VL>(s.MM, pd.core + C_MM * Kpad, vl);
-    load_chunks<Q, VL>(s.MI, pd.core + C_MI * Kpad, vl);
-    load_chunks<Q, VL>(s.MD, pd.core + C_MD * Kpad, vl);
-    load_chunks<Q, VL>(s.IM, pd.core + C_IM * Kpad, vl);
-    load_chunks<Q, VL>(s.II, pd.core + C_II * Kpad, vl);
-    load_chunks<Q, VL>(s.DM, pd.core + C_DM * Kpad, vl);
-    load_chunks<Q, VL>(s.DD, pd.core + C_DD * Kpad, vl);
-    float const RR = xt[X_RR], SN = xt[X_SN], NN = xt[X_NN], SB = xt[X_SB], NB = xt[X_NB], EB = xt[X_EB],
-                JB = xt[X_JB], EJ = xt[X_EJ], JJ = xt[X_JJ], EC = xt[X_EC], CC = xt[X_CC], ET = xt[X_ET],
-                CT = xt[X_CT];
-#pragma unroll
-    for (int j = 0; j < 5; ++j)
-    {
-#pragma unroll
-      for (int q = 0; q < Q; ++q)
-      {
-        s.P[j][q] = CUDART_INF_F;
-        s.Qv[j][q] = CUDART_INF_F;
-      }
-      s.px[j] = CUDART_INF_F;
-    }
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-      s.P[0][q] = SB + s.BM[q]; // row 0: B = SB (viterbi.c:472-473)
-    s.xa = lane == 1 ? EJ : lane == 2 ? EC : CUDART_INF_F;
-    s.xb = lane == 0 ? NN : lane == 1 ? JJ : lane == 2 ? CC : lane == 3 ? RR : CUDART_INF_F;
-    s.px[0] = lane == 0 ? (0.0f + SN) : lane == 3 ? ((-RR) + RR) : CUDART_INF_F;
-
-    // nucleotide stream, one position ahead of the DP row (row l+1's codes are needed in row l)
-    uint32_t const *wp = a.s.reads.words + a.s.reads.seq_word[sq] + (start >> 4);
-    uint32_t word = __ldg(wp) >> (2 * (start & 15));
-    int left = 16 - (start & 15);
-    unsigned H = 0; // bits 2..11: five nucleotides ending at l-1; bits 0..9: ending at l
-#define DCP_NEXT_NT()                                                                            \
-  {                                                                                              \
-    H = ((H << 2) | (word & 3u)) & 0xFFFu;                                                       \
-    word >>= 2;                                                                                  \
-    if (--left == 0)                                                                             \
-    {                                                                                            \
-      word = __ldg(++wp);                                                                        \
-      left = 16;                                                                                 \
-    }                                                                                            \
-  }
-    DCP_NEXT_NT()
-    float E = CUDART_INF_F, x = CUDART_INF_F;
-    bool ok = true;
-    float Mp[Q], Ip[Q], xp = CUDART_INF_F;
-#pragma unroll
-    for (int q = 0; q < Q; ++q)
-    {
-      Mp[q] = CUDART_INF_F;
-      Ip[q] = CUDART_INF_F;
-    }
-#define DCP_ROW(JJ_)                                                                             \
-  {                                                                                              \
-    if (l > L) break;                                                                            \
-    DCP_NEXT_NT()                                                                                \
-    strip_row<Q, W, JJ_>(s, Mp, Ip, xp, pd, (H >> 2) & 1023u, H & 1023u, lane, warp, NB, EB, JB, &sh, l, E, x, ok); \
-    ++l;                                                                                         \
-  }
-    int l = 1;
-    for (;;)
-    {
-      DCP_ROW(1)
-      DCP_ROW(2)
-      DCP_ROW(3)
-      DCP_ROW(4)
-      DCP_ROW(0)
-    }
-#undef DCP_ROW
-#undef DCP_NEXT_NT
-
-    if (warp == W - 1)
-    {
-      float const C = __shfl_sync(FULL_MASK, x, 2);
-      float const R = __shfl_sync(FULL_MASK, x, 3);
-      if (lane == 0)
-      {
-        float const alt = fminf(E + ET, C + CT); // viterbi.c:585-586, 599
-        if (ok)
-        {
-          a.s.out[oidx] = make_float2(R, alt);
-          float const d = alt - R;
-          if (d <= 0.0f && d > -CUDART_INF_F) atomicAdd(a.s.nhits, 1ULL);
-        }
-        else
-          a.redo[atomicAdd(a.nredo, 1ULL)] = oidx; // the exact kernel will produce this pair
-      }
-    }
-    __syncthreads(); // all strips done before the counters are reset
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// One strip per LAUNCH.  Same speculation, but strip w of every pair of a class is one kernel
-// launch and strip w+1 the next one on the same stream: a warp runs one strip of one pair with
-// the plain single-warp pipelined row, reads {M, I, D of the previous strip's last node, running
-// E} of row l from the pair's boundary column in global memory (16 bytes a row, fetched one row
-// ahead) and overwrites it with its own.  No spin waits, no co-scheduling, every launch has the
-// L1 footprint and the register budget of score_reg_kernel<Q,1>; the column costs 32 bytes of
-// HBM traffic per row against 33*32*Q flops.  FIRST/LAST are compile-time: the first strip has
-// no boundary to read, only the last one carries J and C, verifies the speculated B and writes
-// the result (or queues the pair for the exact kernel).
-// ---------------------------------------------------------------------------------------------
-
+// No spin waits, no co-scheduling: every launch has the L1 footprint and the register budget of
+// score_reg_kernel<Q,1>; the column costs 32 bytes of HBM traffic per row against 33*32*Q flops.
+// FIRST/LAST are compile-time: the first strip has no boundary to read, only the last one
+// carries J and C, verifies the speculated B and writes the result (or queues the pair).
 constexpr int LSTRIP_WARPS = 4; // independent (pair, strip) items per CTA
 
 template <int Q, int W, int J, bool FIRST, bool LAST>
