@@ -111,6 +111,8 @@ struct dcpgpu_ctx
   cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
   Mail *d_col = nullptr; // boundary columns of the one-strip-per-launch kernels
   size_t col_cap = 0;
+  size_t col_budget = size_t(16) << 30; // DCPGPU_COL_BUDGET_MB: cap of the boundary columns (tests force chunking)
+  long long lz_slack = 64;              // DCPGPU_LZ_SLACK: slack of a lazily walked path's slot (tests force the rerun)
   bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
   bool timed = false;
   double last_cells = 0;
@@ -585,7 +587,7 @@ int plan_strips(dcpgpu_ctx *ctx, unsigned long long const *count, int maxlen, St
   size_t fr = 0, tot = 0;
   CU(cudaMemGetInfo(&fr, &tot));
   size_t const have = ctx->col_cap * sizeof(Mail);
-  size_t const budget = std::min<size_t>((fr + have) / 2, size_t(16) << 30) / (plan->stride * sizeof(Mail));
+  size_t const budget = std::min<size_t>((fr + have) / 2, ctx->col_budget) / (plan->stride * sizeof(Mail));
   size_t items = total;
   if (total > budget)
   {
@@ -843,6 +845,8 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   {
     char const *v = std::getenv("DCPGPU_SUBWARP");
     ctx->subwarp = !(v && v[0] == '0');
+    if ((v = std::getenv("DCPGPU_COL_BUDGET_MB")) && std::atoll(v) > 0) ctx->col_budget = (size_t)std::atoll(v) << 20;
+    if ((v = std::getenv("DCPGPU_LZ_SLACK"))) ctx->lz_slack = std::atoll(v);
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -1444,7 +1448,8 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     bool const trellis = keep || kernel_class(ctx, pairs[i].profile) == 0;
     ctx->t_xnode_off[(size_t)i + 1] = ctx->t_xnode_off[(size_t)i] + (trellis ? pairs[i].len + 1 : 0);
     ctx->t_node_off[(size_t)i + 1] = ctx->t_node_off[(size_t)i] + (trellis ? (long long)(pairs[i].len + 1) * K : 0);
-    slot_off[(size_t)i + 1] = slot_off[(size_t)i] + (trellis ? 0 : (long long)pairs[i].len + 2 * (long long)K + 64);
+    slot_off[(size_t)i + 1] =
+        slot_off[(size_t)i] + (trellis ? 0 : std::max<long long>(4, (long long)pairs[i].len + 2 * (long long)K + ctx->lz_slack));
   }
   size_t const n = (size_t)npairs;
   if ((rc = ensure(ctx, ctx->d_tpairs, ctx->tpairs_cap, n))) return rc;

@@ -212,3 +212,53 @@ def test_empty_and_invalid(device, golden_dev):
         device.score_pairs(_pairs([(10 ** 6, 0, 0, 1)]))
     with pytest.raises(DcpGpuError):
         device.score_pairs(_pairs([(base, 0, 0, 0)]))  # empty window (window.c BUG_ON)
+
+
+def test_chunked_strip_columns_and_slot_overflow(oracle, node_pool, monkeypatch):
+    """The two rarely taken host paths: boundary columns that do not fit their budget (strip
+    classes take turns, chunk after chunk) and traced paths that outgrow their slot (rerun with
+    exact sizes).  Both are forced through the documented environment hooks; results must not
+    change."""
+    from deciphon_b200.device import Device
+    monkeypatch.setenv("DCPGPU_COL_BUDGET_MB", "1")      # 1 MiB: a few dozen columns per chunk
+    monkeypatch.setenv("DCPGPU_LZ_SLACK", "-1000000")    # 4-step slots: every traced path overflows
+    dev = Device(0)
+    try:
+        rng = np.random.default_rng(321)
+        profs, rows, costs = [], [], {}
+        reads = [synth.random_read(rng, n) for n in (700, 333, 1200, 90)]
+        for K in (300, 700, 1100, 150, 40):
+            prof = synth.synth_profile(rng, K, node_pool)
+            p = dev.add_profile(prof)
+            costs[p] = (K, prof.costs())
+            cons = np.argmax(prof.emission[:K, 20:84], axis=1)
+            cons = np.stack([cons // 16, (cons // 4) % 4, cons % 4], axis=1).reshape(-1).astype(np.uint8)
+            reads.append(synth.mutate(rng, np.concatenate([synth.random_read(rng, 40), cons, synth.random_read(rng, 25)]), 0.05))
+            profs.append(p)
+        dev.set_reads(reads)
+        for p in profs:
+            for ri, x in enumerate(reads):
+                rows.append((p, ri, 0, min(len(x), costs[p][0] * 50)))
+        rows = rows * 3  # more items than a chunk holds
+        nul, alt = dev.score_pairs(_pairs(rows), True, False)
+        hits = []
+        for j, (p, ri, st, ln) in enumerate(rows[: len(rows) // 3]):
+            x = np.ascontiguousarray(reads[ri][st:st + ln])
+            xt = oracle.xtrans(ln, True, False)
+            assert _bits(nul[j:j + 1])[0] == _bits(oracle.null(costs[p][1][0], xt, x).reshape(1))[0], (p, ri, "null")
+            assert _bits(alt[j:j + 1])[0] == _bits(oracle.alt(costs[p][1], xt, x).reshape(1))[0], (p, ri, "alt")
+            lrt = oracle.lrt(nul[j], alt[j])
+            if np.isfinite(lrt) and lrt >= 0:
+                hits.append(rows[j])
+        n3 = len(rows) // 3
+        assert np.array_equal(_bits(nul[:n3]), _bits(nul[n3:2 * n3])) and np.array_equal(_bits(alt[:n3]), _bits(alt[2 * n3:]))
+        assert len(hits) >= 5
+        talt, paths = dev.trace_pairs(_pairs(hits), True, False)
+        for j, (p, ri, st, ln) in enumerate(hits):
+            x = np.ascontiguousarray(reads[ri][st:st + ln])
+            oalt, oxn, ond = oracle.trace(costs[p][1], oracle.xtrans(ln, True, False), x)
+            oids, osz = oracle.unzip(costs[p][0], ln, oxn, ond)
+            assert _bits(talt[j:j + 1])[0] == _bits(oalt.reshape(1))[0]
+            assert np.array_equal(paths[j][0], oids) and np.array_equal(paths[j][1], osz), (p, ri, "path")
+    finally:
+        dev.close()
