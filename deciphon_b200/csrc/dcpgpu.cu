@@ -11,6 +11,7 @@
 #include "score_kernel.cuh"
 #include "strip_kernel.cuh"
 #include "sub_kernel.cuh"
+#include "tail_kernel.cuh"
 #include "trace_argmin.cuh"
 #include "trace_walk.cuh"
 
@@ -68,6 +69,19 @@ struct dcpgpu_ctx
   std::vector<char> h_unsafe; // a cost is negative/NaN: only the generic kernel may run it
   ProfileDesc *d_profiles = nullptr;
   size_t d_profiles_cap = 0;
+  // segmented copies of the profiles of more than 256 nodes (strip_kernel.cuh)
+  std::vector<ProfileDesc> h_segs;
+  std::vector<int> h_seg_first, h_seg_count; // per profile; first = -1: not segmented
+  ProfileDesc *d_segs = nullptr;
+  int *d_seg_first = nullptr;
+  size_t d_segs_cap = 0, d_seg_first_cap = 0;
+  bool segments = true; // DCPGPU_SEGMENTS=0: uniform strips of the whole-profile layout (A/B switch)
+  static constexpr int MAXSEG = 8;
+  cudaEvent_t ev_level[MAXSEG] = {};
+  unsigned long long *d_seg_cursor = nullptr; // [MAXSEG * 17] work cursors of the segment launches
+  int *d_seg_list = nullptr;                  // profile / pair lists of the segment launches
+  long long *d_seg_order = nullptr, *d_seg_colmap = nullptr;
+  size_t seg_list_cap = 0, seg_order_cap = 0, seg_colmap_cap = 0;
   bool profiles_dirty = false;
 
   // upload staging (device)
@@ -219,20 +233,21 @@ int arena_alloc(dcpgpu_ctx *ctx, size_t bytes, void **out)
 
 // ---- pack kernels: .dcp log-probs -> cost-form device layout (protein.c:353-394) -------
 
-__global__ void pack_em_kernel(NodeRef const *nodes, int K, int Q, int VL, int Kpad, float *em, int *bad)
+// Nodes [k0, k0 + K) of a profile of Ktot nodes (the whole profile, or one segment of it).
+__global__ void pack_em_kernel(NodeRef const *nodes, int k0, int K, int Q, int VL, int Kpad, float *em, int *bad)
 {
   // x: node index over Kpad, y: code
   int const k = blockIdx.x * blockDim.x + threadIdx.x;
   int const code = blockIdx.y;
   if (k >= Kpad) return;
   float v = CUDART_INF_F;
-  if (k < K) v = -nodes[k].em[code]; // viterbi_set_match(v, -emission[i], k, i), protein.c:390-391
+  if (k < K) v = -nodes[k0 + k].em[code]; // viterbi_set_match(v, -emission[i], k, i), protein.c:390-391
   if (!(v >= 0.0f)) atomicOr(bad, 1);  // negative or NaN cost: the register kernels' unsigned-order tricks do not apply
   em[(size_t)code * Kpad + layout_pos(k, Q, VL)] = v;
 }
 
-__global__ void pack_core_kernel(NodeRef const *nodes, float const *BMk, int K, int Q, int VL, int Kpad,
-                                 float *core, int *bad)
+__global__ void pack_core_kernel(NodeRef const *nodes, float const *BMk, int k0, int K, int Ktot, int Q, int VL,
+                                 int Kpad, float *core, int *bad)
 {
   int const k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= Kpad) return;
@@ -242,19 +257,20 @@ __global__ void pack_core_kernel(NodeRef const *nodes, float const *BMk, int K, 
     v[i] = CUDART_INF_F;
   if (k < K)
   {
-    v[C_BM] = -BMk[k]; // protein.c:361-364
-    if (k >= 1)
-    { // transitions out of node k-1 land on node k (protein.c:374-381)
-      float const *t = nodes[k - 1].trans;
+    int const g = k0 + k; // node of the whole profile
+    v[C_BM] = -BMk[g]; // protein.c:361-364
+    if (g >= 1)
+    { // transitions out of node g-1 land on node g (protein.c:374-381)
+      float const *t = nodes[g - 1].trans;
       v[C_MM] = -t[0];
       v[C_MD] = -t[2];
       v[C_IM] = -t[3];
       v[C_DM] = -t[5];
       v[C_DD] = -t[6];
     }
-    if (k + 1 < K)
-    { // MI, II stay on node k; node K-1 keeps +INF (protein.c:382-383)
-      float const *t = nodes[k].trans;
+    if (g + 1 < Ktot)
+    { // MI, II stay on node g; node K-1 keeps +INF (protein.c:382-383)
+      float const *t = nodes[g].trans;
       v[C_MI] = -t[1];
       v[C_II] = -t[4];
     }
@@ -359,6 +375,15 @@ int sync_profiles(dcpgpu_ctx *ctx)
   }
   CU(cudaMemcpyAsync(ctx->d_profiles, ctx->h_profiles.data(), n * sizeof(ProfileDesc),
                      cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_seg_first, ctx->d_seg_first_cap, n))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_seg_first, ctx->h_seg_first.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->h_segs.empty())
+  {
+    if ((rc = ensure(ctx, ctx->d_segs, ctx->d_segs_cap, ctx->h_segs.size()))) return rc;
+    CU(cudaMemcpyAsync(ctx->d_segs, ctx->h_segs.data(), ctx->h_segs.size() * sizeof(ProfileDesc),
+                       cudaMemcpyHostToDevice, ctx->stream));
+  }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->profiles_dirty = false;
   return 0;
@@ -622,6 +647,183 @@ int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs a, StripPlan const &p
   });
 }
 
+// ---- segmented profiles: level-by-level launches (strip_kernel.cuh, tail_kernel.cuh) ----------
+// kind of a segment launch: -2 = first full segment, -1 = later full segment, 0..15 = tail class
+// (0..3: full warp, Q = 5..8; 4..7: 16 lanes; 8..11: 8 lanes; 12..15: 4 lanes).
+int tail_class(ProfileDesc const &g)
+{
+  int const base = g.VL == 32 ? 0 : g.VL == 16 ? 4 : g.VL == 8 ? 8 : 12;
+  return base + (g.Q - 5);
+}
+
+int launch_segment(dcpgpu_ctx *ctx, int kind, StripArgs const &a, cudaStream_t st)
+{
+  auto go = [&](auto kernel, int per_cta) -> int {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+    unsigned long long const want = (a.s.nitems + per_cta - 1) / per_cta;
+    unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
+    kernel<<<grid, 128, 0, st>>>(a);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+    return 0;
+  };
+  static_assert(LSTRIP_WARPS == 4 && SUB_GROUPS == 4, "128-thread CTAs");
+  switch (kind)
+  {
+  case -2: return go(score_lstrip_kernel<8, 1, true, false>, 4);
+  case -1: return go(score_lstrip_kernel<8, 1, false, false>, 4);
+  case 0: return go(score_lstrip_kernel<5, 1, false, true>, 4);
+  case 1: return go(score_lstrip_kernel<6, 1, false, true>, 4);
+  case 2: return go(score_lstrip_kernel<7, 1, false, true>, 4);
+  case 3: return go(score_lstrip_kernel<8, 1, false, true>, 4);
+  case 4: return go(score_subtail_kernel<5, 2>, 8);
+  case 5: return go(score_subtail_kernel<6, 2>, 8);
+  case 6: return go(score_subtail_kernel<7, 2>, 8);
+  case 7: return go(score_subtail_kernel<8, 2>, 8);
+  case 8: return go(score_subtail_kernel<5, 4>, 16);
+  case 9: return go(score_subtail_kernel<6, 4>, 16);
+  case 10: return go(score_subtail_kernel<7, 4>, 16);
+  case 11: return go(score_subtail_kernel<8, 4>, 16);
+  case 12: return go(score_subtail_kernel<5, 8>, 32);
+  case 13: return go(score_subtail_kernel<6, 8>, 32);
+  case 14: return go(score_subtail_kernel<7, 8>, 32);
+  case 15: return go(score_subtail_kernel<8, 8>, 32);
+  default: return fail(ctx, DCPGPU_EINVAL, "bad segment kind");
+  }
+}
+
+struct SegLaunch
+{
+  int kind, level;
+  size_t off, count; // range of the entry lists
+};
+
+struct SegPlan
+{
+  bool grid = false; // entries are profiles (x nseq reads) or explicit pairs
+  std::vector<SegLaunch> launches;
+  size_t stride = 0;
+  int levels = 0;
+};
+
+// entries[r] = {profile id, key}: key = the profile id again (grid) or the pair index (pairs);
+// r is the entry's column rank.  Builds and uploads the per-launch lists.  Returns 1 if the
+// boundary columns would not fit the budget (the caller falls back to uniform strips).
+int prepare_segments(dcpgpu_ctx *ctx, bool grid, std::vector<std::pair<int, long long>> const &entries, size_t per_entry,
+                     int maxlen, SegPlan *plan)
+{
+  plan->grid = grid;
+  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
+  size_t const ncols = entries.size() * per_entry;
+  {
+    size_t fr = 0, tot = 0;
+    CU(cudaMemGetInfo(&fr, &tot));
+    size_t const have = ctx->col_cap * sizeof(Mail);
+    size_t const budget = std::min<size_t>((fr + have) / 2, ctx->col_budget) / (plan->stride * sizeof(Mail));
+    if (ncols > budget) return 1;
+  }
+  if (ncols * plan->stride > ctx->col_cap)
+  {
+    if (ctx->d_col) CU(cudaFree(ctx->d_col));
+    ctx->d_col = nullptr;
+    ctx->col_cap = 0;
+    CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_col), ncols * plan->stride * sizeof(Mail)));
+    ctx->col_cap = ncols * plan->stride;
+  }
+  // bucket the ranks by (level, kind)
+  std::vector<std::vector<size_t>> full(dcpgpu_ctx::MAXSEG), tail((size_t)dcpgpu_ctx::MAXSEG * 16);
+  int levels = 0;
+  for (size_t r = 0; r < entries.size(); ++r)
+  {
+    int const p = entries[r].first, nseg = ctx->h_seg_count[(size_t)p], first = ctx->h_seg_first[(size_t)p];
+    if (first < 0 || nseg < 2 || nseg > dcpgpu_ctx::MAXSEG) return fail(ctx, DCPGPU_ESTATE, "segments: profile is not segmented");
+    for (int lv = 0; lv + 1 < nseg; ++lv) full[(size_t)lv].push_back(r);
+    tail[(size_t)(nseg - 1) * 16 + (size_t)tail_class(ctx->h_segs[(size_t)(first + nseg - 1)])].push_back(r);
+    levels = std::max(levels, nseg);
+  }
+  plan->levels = levels;
+  std::vector<int> list;
+  std::vector<long long> order, colmap;
+  auto add = [&](int kind, int level, std::vector<size_t> const &ranks) {
+    if (ranks.empty()) return;
+    plan->launches.push_back(SegLaunch{kind, level, colmap.size(), ranks.size()});
+    for (size_t r : ranks)
+    {
+      list.push_back(entries[r].first);
+      order.push_back(entries[r].second);
+      colmap.push_back((long long)r);
+    }
+  };
+  for (int lv = 0; lv < levels; ++lv)
+  {
+    for (int tc = 0; tc < 16; ++tc) add(tc, lv, tail[(size_t)lv * 16 + (size_t)tc]);
+    add(lv == 0 ? -2 : -1, lv, full[(size_t)lv]);
+  }
+  int rc;
+  size_t const m = colmap.size();
+  if ((rc = ensure(ctx, ctx->d_seg_list, ctx->seg_list_cap, m))) return rc;
+  if ((rc = ensure(ctx, ctx->d_seg_order, ctx->seg_order_cap, m))) return rc;
+  if ((rc = ensure(ctx, ctx->d_seg_colmap, ctx->seg_colmap_cap, m))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_seg_list, list.data(), m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_seg_order, order.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_seg_colmap, colmap.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_seg_cursor, 0, dcpgpu_ctx::MAXSEG * 17 * sizeof(unsigned long long), ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream)); // the vectors are locals
+  return 0;
+}
+
+// After fork_streams: the full segments of level s run in order on one side stream; the tails of
+// level s (they only need the full segments up to s-1) on the other side streams.
+int launch_segments(dcpgpu_ctx *ctx, SegPlan const &plan, ScoreArgs const &a0)
+{
+  cudaStream_t const chain = ctx->side[0];
+  int next_side = 1;
+  size_t i = 0;
+  for (int lv = 0; lv < plan.levels; ++lv)
+  {
+    for (; i < plan.launches.size() && plan.launches[i].level == lv; ++i)
+    {
+      SegLaunch const &L = plan.launches[i];
+      StripArgs sa{};
+      sa.s = a0;
+      sa.redo = ctx->d_redo;
+      sa.nredo = ctx->d_counters + SLOT_NREDO;
+      sa.col = ctx->d_col;
+      sa.col_stride = plan.stride;
+      sa.strip = 0;
+      sa.item0 = 0;
+      sa.segs = ctx->d_segs;
+      sa.seg_first = ctx->d_seg_first;
+      sa.level = lv;
+      sa.colmap = ctx->d_seg_colmap + L.off;
+      sa.s.counter = ctx->d_seg_cursor + (size_t)lv * 17 + (size_t)(L.kind < 0 ? 16 : L.kind);
+      if (plan.grid)
+      {
+        sa.s.class_profiles = ctx->d_seg_list + L.off;
+        sa.s.nitems = (unsigned long long)L.count * (unsigned long long)a0.nseq;
+      }
+      else
+      {
+        sa.s.order = ctx->d_seg_order + L.off;
+        sa.s.nitems = L.count;
+      }
+      cudaStream_t st = chain;
+      if (L.kind >= 0)
+      { // a tail: any other side stream, after the previous level's full segments
+        st = ctx->side[next_side];
+        next_side = next_side % (dcpgpu_ctx::NSIDE - 1) + 1;
+        CU(cudaStreamWaitEvent(st, ctx->ev_level[lv - 1], 0));
+      }
+      int const rc = launch_segment(ctx, L.kind, sa, st);
+      if (rc) return rc;
+      if (L.kind < 0) CU(cudaEventRecord(ctx->ev_level[lv], chain));
+    }
+  }
+  return 0;
+}
+
 // Pairs whose speculation failed (d_redo[0..n)): run them on the exact multi-warp kernels.
 // `to_pair` maps a result index to the window it stands for.
 template <class F>
@@ -845,6 +1047,8 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   {
     char const *v = std::getenv("DCPGPU_SUBWARP");
     ctx->subwarp = !(v && v[0] == '0');
+    v = std::getenv("DCPGPU_SEGMENTS");
+    ctx->segments = !(v && v[0] == '0');
     if ((v = std::getenv("DCPGPU_COL_BUDGET_MB")) && std::atoll(v) > 0) ctx->col_budget = (size_t)std::atoll(v) << 20;
     if ((v = std::getenv("DCPGPU_LZ_SLACK"))) ctx->lz_slack = std::atoll(v);
   }
@@ -858,6 +1062,10 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming);
   }
+  for (int i = 0; i < dcpgpu_ctx::MAXSEG; ++i)
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_level[i], cudaEventDisableTiming);
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_seg_cursor), dcpgpu_ctx::MAXSEG * 17 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_counters), NSLOTS * sizeof(unsigned long long));
   if (e != cudaSuccess)
@@ -903,6 +1111,14 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_dump);
   cudaFree(ctx->d_hit_idx);
   cudaFree(ctx->d_redo);
+  cudaFree(ctx->d_segs);
+  cudaFree(ctx->d_seg_first);
+  cudaFree(ctx->d_seg_cursor);
+  cudaFree(ctx->d_seg_list);
+  cudaFree(ctx->d_seg_order);
+  cudaFree(ctx->d_seg_colmap);
+  for (auto e : ctx->ev_level)
+    if (e) cudaEventDestroy(e);
   cudaFree(ctx->d_col);
   cudaFree(ctx->d_redo_pairs);
   cudaFree(ctx->d_redo_order);
@@ -1037,7 +1253,7 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   d.K = K;
   layout_shape(K, &d.Q, &d.W, &d.VL, ctx->subwarp);
   d.Kpad = d.VL * d.Q;
-  d.pad_ = 0;
+  d.Kfull = K;
   void *pem = nullptr, *pcore = nullptr, *pnb = nullptr;
   int rc;
   if ((rc = arena_alloc(ctx, (size_t)NCODES * d.Kpad * sizeof(float), &pem))) return rc;
@@ -1064,13 +1280,44 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   dim3 const grid((d.Kpad + 127) / 128, NCODES);
   int *d_bad = reinterpret_cast<int *>(ctx->d_counters + SLOT_BAD);
   CU(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-  pack_em_kernel<<<grid, 128, 0, ctx->stream>>>(drefs, K, d.Q, VL, d.Kpad, static_cast<float *>(pem), d_bad);
+  pack_em_kernel<<<grid, 128, 0, ctx->stream>>>(drefs, 0, K, d.Q, VL, d.Kpad, static_cast<float *>(pem), d_bad);
   pack_core_kernel<<<(d.Kpad + 127) / 128, 128, 0, ctx->stream>>>(
-      drefs, reinterpret_cast<float const *>(ctx->d_stage + o_bm), K, d.Q, VL, d.Kpad, static_cast<float *>(pcore), d_bad);
+      drefs, reinterpret_cast<float const *>(ctx->d_stage + o_bm), 0, K, K, d.Q, VL, d.Kpad, static_cast<float *>(pcore), d_bad);
   pack_nulbg_kernel<<<(NCODES + 127) / 128, 128, 0, ctx->stream>>>(
       reinterpret_cast<float const *>(ctx->d_stage + o_nul), reinterpret_cast<float const *>(ctx->d_stage + o_bg),
       static_cast<float2 *>(pnb), d_bad);
   CU(cudaGetLastError());
+  // Profiles the strip kernels run are also stored as segments: 256 nodes each in the Q = 8
+  // full-warp layout, the tail in the layout a profile of its size would get (strip_kernel.cuh).
+  int seg_first = -1, seg_count = 0;
+  if (ctx->segments && d.W > 1 && d.Q <= MAXQ_REG)
+  {
+    seg_first = (int)ctx->h_segs.size();
+    for (int k0 = 0; k0 < K; k0 += 256)
+    {
+      ProfileDesc g;
+      g.K = std::min(256, K - k0);
+      g.Kfull = K;
+      if (k0 + 256 < K) { g.Q = 8; g.W = 1; g.VL = 32; }
+      else layout_shape(g.K, &g.Q, &g.W, &g.VL, true);
+      g.Kpad = g.VL * g.Q;
+      void *sem = nullptr, *score = nullptr;
+      if ((rc = arena_alloc(ctx, (size_t)NCODES * g.Kpad * sizeof(float), &sem))) return rc;
+      if ((rc = arena_alloc(ctx, (size_t)C_ROWS * g.Kpad * sizeof(float), &score))) return rc;
+      g.em = static_cast<float *>(sem);
+      g.core = static_cast<float *>(score);
+      g.nulbg = d.nulbg;
+      dim3 const sgrid((g.Kpad + 127) / 128, NCODES);
+      pack_em_kernel<<<sgrid, 128, 0, ctx->stream>>>(drefs, k0, g.K, g.Q, g.VL, g.Kpad, static_cast<float *>(sem), d_bad);
+      pack_core_kernel<<<(g.Kpad + 127) / 128, 128, 0, ctx->stream>>>(
+          drefs, reinterpret_cast<float const *>(ctx->d_stage + o_bm), k0, g.K, K, g.Q, g.VL, g.Kpad,
+          static_cast<float *>(score), d_bad);
+      CU(cudaGetLastError());
+      ctx->launches += 2;
+      ctx->h_segs.push_back(g);
+      ++seg_count;
+    }
+  }
   int h_bad = 0;
   CU(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->launches += 3;
@@ -1079,6 +1326,8 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
 
   ctx->h_profiles.push_back(d);
   ctx->h_unsafe.push_back(h_bad != 0);
+  ctx->h_seg_first.push_back(h_bad ? -1 : seg_first);
+  ctx->h_seg_count.push_back(h_bad ? 0 : seg_count);
   ctx->profiles_dirty = true;
   if (profile_index) *profile_index = (int32_t)ctx->h_profiles.size() - 1;
   return 0;
@@ -1198,7 +1447,23 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
+  // profiles of more than 256 nodes: segment by segment if the boundary columns fit, else uniform strips
+  SegPlan seg;
+  bool seg_ok = false;
+  if (ctx->segments)
+  {
+    std::vector<std::pair<int, long long>> entries;
+    for (int c = 9; c <= 20; ++c)
+      for (long long i : bucket[(size_t)c]) entries.push_back({pairs[i].profile, i});
+    if (!entries.empty())
+    {
+      rc = prepare_segments(ctx, false, entries, 1, maxlen, &seg);
+      if (rc != 0 && rc != 1) return rc;
+      seg_ok = rc == 0;
+    }
+  }
   StripPlan plan;
+  if (!seg_ok)
   {
     unsigned long long count[NCLASS];
     for (int c = 0; c < NCLASS; ++c) count[c] = first[c + 1] - first[c];
@@ -1209,11 +1474,23 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
 
   if ((rc = fork_streams(ctx))) return rc;
+  if (seg_ok)
+  {
+    ScoreArgs a{};
+    a.profiles = ctx->d_profiles;
+    a.reads = reads_view(ctx);
+    a.xt = ctx->d_xt[flags & 3u];
+    a.pairs = ctx->d_pairs;
+    a.out = ctx->d_out;
+    a.nhits = ctx->d_counters + SLOT_NHITS;
+    if ((rc = launch_segments(ctx, seg, a))) return rc;
+    any_strip = true;
+  }
   for (int ci = 0; ci < NCLASS; ++ci)
   {
     int const c = launch_order(ci); // longest pairs first: their tail hides under the rest
     size_t const n = first[c + 1] - first[c];
-    if (!n) continue;
+    if (!n || (seg_ok && c >= 9 && c <= 20)) continue;
     ScoreArgs a{};
     a.profiles = ctx->d_profiles;
     a.reads = reads_view(ctx);
@@ -1299,7 +1576,22 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     for (int c = 9; c <= 20; ++c) strip_items += (first[c + 1] - first[c]) * (size_t)nseq;
     if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, strip_items))) return rc;
   }
+  SegPlan seg;
+  bool seg_ok = false;
+  if (ctx->segments)
+  {
+    std::vector<std::pair<int, long long>> entries;
+    for (int c = 9; c <= 20; ++c)
+      for (int p : bucket[(size_t)c]) entries.push_back({p, (long long)p});
+    if (!entries.empty())
+    {
+      rc = prepare_segments(ctx, true, entries, (size_t)nseq, ctx->maxlen, &seg);
+      if (rc != 0 && rc != 1) return rc;
+      seg_ok = rc == 0;
+    }
+  }
   StripPlan plan;
+  if (!seg_ok)
   {
     unsigned long long count[NCLASS];
     for (int c = 0; c < NCLASS; ++c) count[c] = (unsigned long long)(first[c + 1] - first[c]) * (unsigned long long)nseq;
@@ -1312,11 +1604,25 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
 
   // longest pairs first (generic, then W = 8 .. 1): their tail hides under the classes that follow
   if ((rc = fork_streams(ctx))) return rc;
+  if (seg_ok)
+  {
+    ScoreArgs a{};
+    a.profiles = ctx->d_profiles;
+    a.reads = reads_view(ctx);
+    a.xt = ctx->d_xt[flags & 3u];
+    a.prof0 = prof0;
+    a.seq0 = seq0;
+    a.nseq = nseq;
+    a.out = ctx->d_out;
+    a.nhits = ctx->d_counters + SLOT_NHITS;
+    if ((rc = launch_segments(ctx, seg, a))) return rc;
+    any_strip = true;
+  }
   for (int ci = 0; ci < NCLASS; ++ci)
   {
     int const c = launch_order(ci);
     size_t const n = first[c + 1] - first[c];
-    if (!n) continue;
+    if (!n || (seg_ok && c >= 9 && c <= 20)) continue;
     ScoreArgs a{};
     a.profiles = ctx->d_profiles;
     a.reads = reads_view(ctx);

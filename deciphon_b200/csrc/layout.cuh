@@ -33,7 +33,7 @@ struct ProfileDesc
   int Kpad; // VL * Q
   int VL;   // virtual lanes a row is striped over: 32 * W, or 16/8/4 for profiles of at most
             // 128/64/32 nodes (two/four/eight pairs share a warp, sub_kernel.cuh)
-  int pad_;
+  int Kfull; // nodes of the whole profile when this describes one segment of it (strip_kernel.cuh), else K
 };
 
 __host__ __device__ inline int layout_pos(int k, int Q, int VL)

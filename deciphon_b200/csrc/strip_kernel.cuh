@@ -39,7 +39,24 @@ struct StripArgs
   unsigned long long col_stride;
   int strip;                     // which strip of the pair this launch runs
   unsigned long long item0;      // first item of this launch's range ([item0, s.nitems))
+  // segmented profiles (below): descriptor of segment `level` of profile p at segs[seg_first[p] + level];
+  // column of an item: colmap[item] (explicit pairs) or colmap[profile slot] * nseq + read (grid)
+  ProfileDesc const *segs;
+  int const *seg_first;
+  int level;
+  long long const *colmap;
 };
+
+// Segmented profiles.  With one strip per launch nothing forces the strips of a profile to share
+// a shape, so a profile of more than 256 nodes is ALSO stored as segments: 256 nodes each in the
+// Q = 8 full-warp layout (the most efficient row there is), and a tail of 1..256 nodes in the
+// layout a stand-alone profile of that size would get (sub-warp for <= 128 nodes).  The score
+// pass runs the segments level by level; the exact kernels (redo, trace) keep using the
+// whole-profile layout.  K = 300: 363 + 330/4 instructions per row instead of 2 x 290.
+__device__ __forceinline__ ProfileDesc strip_desc(StripArgs const &a, int p)
+{
+  return a.segs ? a.segs[a.seg_first[p] + a.level] : a.s.profiles[p];
+}
 
 // d_lazy with a fixed incoming value for the head lane (the previous strip's final D)
 template <int Q>
@@ -189,7 +206,7 @@ __global__ void __launch_bounds__(32 * LSTRIP_WARPS, Q >= 6 ? 2 : 3) score_lstri
     unsigned long long item = 0;
     if (lane == 0) item = atomicAdd(a.s.counter, 1ULL);
     item = __shfl_sync(FULL_MASK, item, 0);
-    Mail *const col = a.col + (size_t)item * a.col_stride; // columns are indexed inside the range
+    size_t colidx = (size_t)item; // columns are indexed inside the range unless a map is given
     item += a.item0;
     if (item >= a.s.nitems) break;
 
@@ -200,6 +217,7 @@ __global__ void __launch_bounds__(32 * LSTRIP_WARPS, Q >= 6 ? 2 : 3) score_lstri
       oidx = a.s.order[item];
       Pair const pr = a.s.pairs[oidx];
       p = pr.profile; sq = pr.seq; start = pr.start; L = pr.len;
+      if (a.colmap) colidx = (size_t)a.colmap[item];
     }
     else
     {
@@ -210,10 +228,12 @@ __global__ void __launch_bounds__(32 * LSTRIP_WARPS, Q >= 6 ? 2 : 3) score_lstri
       start = 0;
       oidx = (long long)(p - a.s.prof0) * a.s.nseq + si;
       L = -1;
+      if (a.colmap) colidx = (size_t)a.colmap[pi] * (unsigned)a.s.nseq + si;
     }
-    ProfileDesc const pd = a.s.profiles[p];
-    if (L < 0) L = min(min(pd.K * 50, 100000), a.s.reads.seq_len[sq]);
+    ProfileDesc const pd = strip_desc(a, p);
+    if (L < 0) L = min(min(pd.Kfull * 50, 100000), a.s.reads.seq_len[sq]);
     float const *xt = a.s.xt + (size_t)L * X_STRIDE;
+    Mail *const col = a.col + colidx * a.col_stride;
 
     Lane<Q> s;
     int const Kpad = pd.Kpad;
