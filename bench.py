@@ -40,6 +40,16 @@ from deciphon_b200 import synth  # noqa: E402
 OPS_PER_CELL = 33  # fp32 add/min per DP cell, factored recurrence
 
 
+def measured_traffic():
+    """DRAM bytes of the score pass of one step at the default workload, from the committed ncu
+    capture (dram__bytes_read.sum + dram__bytes_write.sum; profiles/README.md).  None if absent."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic_v13.json")) as f:
+            return float(json.load(f)["score_pass_dram_bytes_per_step"])
+    except Exception:
+        return None
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -335,6 +345,9 @@ def run_b200(args, rank, local_rank, world):
             peak = 148 * 128 * 1.965e9 / 1e12
             peak_src = "fallback: nominal 148 SM x 128 lanes x 1.965 GHz"
         achieved = OPS_PER_CELL * stats["cells"] / (stats["score_ms"] * 1e-3) / 1e12
+        # DRAM bytes of one step's score pass, ncu capture of this workload (default sizes, one GPU)
+        traffic_bytes = measured_traffic() if (world == 1 and args.profiles == 20000 and args.reads_per_step == 48
+                                               and args.read_len == 2000) else None
         line = {
             "metric": "GCUPS (nt x node DP cells/s), Pfam-scale scan", "value": gcups, "unit": "GCUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -346,8 +359,8 @@ def run_b200(args, rank, local_rank, world):
                     "reads_per_s": args.steps * R / e2e_s},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32-alu (non-tensor add/min issue; not hbm, not tensor)", "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                         "kernel": "score pass = score_sub_kernel<Q,G> (K<=128) + score_reg_kernel<Q,1> (K<=256) + score_strip_kernel<Q,W> (K<=2048, exact redo of failed speculation) + generic_kernel<false> (rest), rank 0",
+                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic_bytes,
+                         "kernel": "score pass = score_sub_kernel<Q,G> (K<=128) + score_reg_kernel<Q,1> (K<=256) + score_lstrip/subtail_kernel over 256-node segments (K<=2048, exact redo of failed speculation) + generic_kernel<false> (rest), rank 0",
                          "ops_per_cell": OPS_PER_CELL, "kernel_gcups": stats["cells"] / (stats["score_ms"] * 1e-3) / 1e9,
                          "kernel_ms_per_step": stats["score_ms"] / args.steps, "peak_source": peak_src,
                          "hbm_gbs_measured": _measured_peaks().get("hbm_gbs")},

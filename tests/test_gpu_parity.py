@@ -262,3 +262,55 @@ def test_chunked_strip_columns_and_slot_overflow(oracle, node_pool, monkeypatch)
             assert np.array_equal(paths[j][0], oids) and np.array_equal(paths[j][1], osz), (p, ri, "path")
     finally:
         dev.close()
+
+
+def test_layout_variants_agree(node_pool, monkeypatch):
+    """The same synthetic database through the three layout choices the library can make --
+    default (sub-warp kernels for K <= 128, segmented profiles for K > 256), whole-warp small
+    profiles, uniform strips -- must give bit-identical scores, the same hit list and identical
+    paths: the layout only decides which kernels run."""
+    from deciphon_b200.device import Device
+    rng0 = np.random.default_rng(77)
+    sizes = np.concatenate([rng0.integers(5, 130, 40), rng0.integers(130, 257, 25), rng0.integers(257, 1300, 45),
+                            [2048, 2049, 256, 257, 128, 129, 512, 513, 33, 32]])
+    nprof, R, L = len(sizes), 24, 900
+    results = []
+    for env in ({}, {"DCPGPU_SUBWARP": "0"}, {"DCPGPU_SEGMENTS": "0"}):
+        for k in ("DCPGPU_SUBWARP", "DCPGPU_SEGMENTS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        dev = Device(0)
+        try:
+            rng = np.random.default_rng(78)
+            first = dev.pool_add(node_pool.emission, node_pool.trans)
+            ids_of = []
+            for K in sizes:
+                ids, bmk = synth.synth_profile_nodes(rng, int(K), node_pool)
+                dev.profile_add(int(K), bmk, node_pool.null_emission, node_pool.bg_emission, ids + first)
+                ids_of.append(ids)
+            reads = []
+            for i in range(R):
+                x = synth.random_read(rng, L)
+                if i % 3 == 0:  # embed a consensus so that hits and multi-row B deviations exist
+                    cons = synth.consensus_dna(node_pool, ids_of[(7 * i) % nprof])[: L - 100]
+                    x = np.concatenate([x[:50], cons, x[50 + len(cons):]])[:L]
+                reads.append(synth.mutate(rng, x, 0.05)[:L])
+            dev.set_reads(reads)
+            dev.score_grid(0, nprof, 0, R)
+            nul, alt = dev.scores_fetch(nprof * R)
+            hits = dev.hits_fetch()
+            pr = np.zeros(len(hits), dtype=PAIR_DTYPE)
+            pr["profile"] = hits // R
+            pr["seq"] = hits % R
+            lens = np.array([len(x) for x in reads])
+            pr["len"] = np.minimum(np.minimum(sizes[hits // R] * 50, 100000), lens[hits % R])
+            talt, off, ids, sz = dev.trace_pairs_flat(pr)
+            results.append((_bits(nul), _bits(alt), hits, _bits(talt), off, ids[: off[-1]], sz[: off[-1]], dev.last_redo()))
+        finally:
+            dev.close()
+    base = results[0]
+    assert len(base[2]) >= 10
+    for other in results[1:]:
+        for a, b in zip(base[:7], other[:7]):
+            assert np.array_equal(a, b)
