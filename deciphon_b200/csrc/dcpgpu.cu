@@ -700,30 +700,36 @@ struct SegLaunch
   size_t off, count; // range of the entry lists
 };
 
-struct SegPlan
+struct SegChunk
 {
-  bool grid = false; // entries are profiles (x nseq reads) or explicit pairs
   std::vector<SegLaunch> launches;
-  size_t stride = 0;
   int levels = 0;
 };
 
+struct SegPlan
+{
+  bool grid = false; // entries are profiles (x nseq reads) or explicit pairs
+  std::vector<SegChunk> chunks; // each fits the boundary-column budget; they run one after the other
+  size_t stride = 0;
+};
+
 // entries[r] = {profile id, key}: key = the profile id again (grid) or the pair index (pairs);
-// r is the entry's column rank.  Builds and uploads the per-launch lists.  Returns 1 if the
-// boundary columns would not fit the budget (the caller falls back to uniform strips).
+// inside a chunk the entry's position is its column rank.  Builds and uploads the per-launch
+// lists.
 int prepare_segments(dcpgpu_ctx *ctx, bool grid, std::vector<std::pair<int, long long>> const &entries, size_t per_entry,
                      int maxlen, SegPlan *plan)
 {
   plan->grid = grid;
   plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
-  size_t const ncols = entries.size() * per_entry;
+  size_t chunk_entries = entries.size();
   {
     size_t fr = 0, tot = 0;
     CU(cudaMemGetInfo(&fr, &tot));
     size_t const have = ctx->col_cap * sizeof(Mail);
     size_t const budget = std::min<size_t>((fr + have) / 2, ctx->col_budget) / (plan->stride * sizeof(Mail));
-    if (ncols > budget) return 1;
+    chunk_entries = std::min(chunk_entries, std::max<size_t>(budget / std::max<size_t>(per_entry, 1), 1));
   }
+  size_t const ncols = chunk_entries * per_entry;
   if (ncols * plan->stride > ctx->col_cap)
   {
     if (ctx->d_col) CU(cudaFree(ctx->d_col));
@@ -732,34 +738,39 @@ int prepare_segments(dcpgpu_ctx *ctx, bool grid, std::vector<std::pair<int, long
     CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_col), ncols * plan->stride * sizeof(Mail)));
     ctx->col_cap = ncols * plan->stride;
   }
-  // bucket the ranks by (level, kind)
-  std::vector<std::vector<size_t>> full(dcpgpu_ctx::MAXSEG), tail((size_t)dcpgpu_ctx::MAXSEG * 16);
-  int levels = 0;
-  for (size_t r = 0; r < entries.size(); ++r)
-  {
-    int const p = entries[r].first, nseg = ctx->h_seg_count[(size_t)p], first = ctx->h_seg_first[(size_t)p];
-    if (first < 0 || nseg < 2 || nseg > dcpgpu_ctx::MAXSEG) return fail(ctx, DCPGPU_ESTATE, "segments: profile is not segmented");
-    for (int lv = 0; lv + 1 < nseg; ++lv) full[(size_t)lv].push_back(r);
-    tail[(size_t)(nseg - 1) * 16 + (size_t)tail_class(ctx->h_segs[(size_t)(first + nseg - 1)])].push_back(r);
-    levels = std::max(levels, nseg);
-  }
-  plan->levels = levels;
   std::vector<int> list;
   std::vector<long long> order, colmap;
-  auto add = [&](int kind, int level, std::vector<size_t> const &ranks) {
-    if (ranks.empty()) return;
-    plan->launches.push_back(SegLaunch{kind, level, colmap.size(), ranks.size()});
-    for (size_t r : ranks)
-    {
-      list.push_back(entries[r].first);
-      order.push_back(entries[r].second);
-      colmap.push_back((long long)r);
-    }
-  };
-  for (int lv = 0; lv < levels; ++lv)
+  for (size_t e0 = 0; e0 < entries.size(); e0 += chunk_entries)
   {
-    for (int tc = 0; tc < 16; ++tc) add(tc, lv, tail[(size_t)lv * 16 + (size_t)tc]);
-    add(lv == 0 ? -2 : -1, lv, full[(size_t)lv]);
+    size_t const e1 = std::min(entries.size(), e0 + chunk_entries);
+    SegChunk chunk;
+    // bucket the ranks by (level, kind)
+    std::vector<std::vector<size_t>> full(dcpgpu_ctx::MAXSEG), tail((size_t)dcpgpu_ctx::MAXSEG * 16);
+    for (size_t r = e0; r < e1; ++r)
+    {
+      int const p = entries[r].first, nseg = ctx->h_seg_count[(size_t)p], first = ctx->h_seg_first[(size_t)p];
+      if (first < 0 || nseg < 2 || nseg > dcpgpu_ctx::MAXSEG)
+        return fail(ctx, DCPGPU_ESTATE, "segments: profile is not segmented");
+      for (int lv = 0; lv + 1 < nseg; ++lv) full[(size_t)lv].push_back(r);
+      tail[(size_t)(nseg - 1) * 16 + (size_t)tail_class(ctx->h_segs[(size_t)(first + nseg - 1)])].push_back(r);
+      chunk.levels = std::max(chunk.levels, nseg);
+    }
+    auto add = [&](int kind, int level, std::vector<size_t> const &ranks) {
+      if (ranks.empty()) return;
+      chunk.launches.push_back(SegLaunch{kind, level, colmap.size(), ranks.size()});
+      for (size_t r : ranks)
+      {
+        list.push_back(entries[r].first);
+        order.push_back(entries[r].second);
+        colmap.push_back((long long)(r - e0));
+      }
+    };
+    for (int lv = 0; lv < chunk.levels; ++lv)
+    {
+      for (int tc = 0; tc < 16; ++tc) add(tc, lv, tail[(size_t)lv * 16 + (size_t)tc]);
+      add(lv == 0 ? -2 : -1, lv, full[(size_t)lv]);
+    }
+    plan->chunks.push_back(std::move(chunk));
   }
   int rc;
   size_t const m = colmap.size();
@@ -769,56 +780,66 @@ int prepare_segments(dcpgpu_ctx *ctx, bool grid, std::vector<std::pair<int, long
   CU(cudaMemcpyAsync(ctx->d_seg_list, list.data(), m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_seg_order, order.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_seg_colmap, colmap.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemsetAsync(ctx->d_seg_cursor, 0, dcpgpu_ctx::MAXSEG * 17 * sizeof(unsigned long long), ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // the vectors are locals
   return 0;
 }
 
-// After fork_streams: the full segments of level s run in order on one side stream; the tails of
-// level s (they only need the full segments up to s-1) on the other side streams.
+// Called with the side streams forked.  The full segments of level s run in order on one side
+// stream; the tails of level s (they only need the full segments up to s-1) on the other side
+// streams.  Chunks share the column buffer, so the streams are joined between them.
 int launch_segments(dcpgpu_ctx *ctx, SegPlan const &plan, ScoreArgs const &a0)
 {
   cudaStream_t const chain = ctx->side[0];
-  int next_side = 1;
-  size_t i = 0;
-  for (int lv = 0; lv < plan.levels; ++lv)
+  int rc;
+  for (size_t ci = 0; ci < plan.chunks.size(); ++ci)
   {
-    for (; i < plan.launches.size() && plan.launches[i].level == lv; ++i)
+    SegChunk const &chunk = plan.chunks[ci];
+    if (ci > 0)
     {
-      SegLaunch const &L = plan.launches[i];
-      StripArgs sa{};
-      sa.s = a0;
-      sa.redo = ctx->d_redo;
-      sa.nredo = ctx->d_counters + SLOT_NREDO;
-      sa.col = ctx->d_col;
-      sa.col_stride = plan.stride;
-      sa.strip = 0;
-      sa.item0 = 0;
-      sa.segs = ctx->d_segs;
-      sa.seg_first = ctx->d_seg_first;
-      sa.level = lv;
-      sa.colmap = ctx->d_seg_colmap + L.off;
-      sa.s.counter = ctx->d_seg_cursor + (size_t)lv * 17 + (size_t)(L.kind < 0 ? 16 : L.kind);
-      if (plan.grid)
+      if ((rc = join_streams(ctx))) return rc;
+    }
+    CU(cudaMemsetAsync(ctx->d_seg_cursor, 0, dcpgpu_ctx::MAXSEG * 17 * sizeof(unsigned long long), ctx->stream));
+    if ((rc = fork_streams(ctx))) return rc; // (re)fork: the side streams see the zeroed cursors
+    int next_side = 1;
+    size_t i = 0;
+    for (int lv = 0; lv < chunk.levels; ++lv)
+    {
+      for (; i < chunk.launches.size() && chunk.launches[i].level == lv; ++i)
       {
-        sa.s.class_profiles = ctx->d_seg_list + L.off;
-        sa.s.nitems = (unsigned long long)L.count * (unsigned long long)a0.nseq;
+        SegLaunch const &L = chunk.launches[i];
+        StripArgs sa{};
+        sa.s = a0;
+        sa.redo = ctx->d_redo;
+        sa.nredo = ctx->d_counters + SLOT_NREDO;
+        sa.col = ctx->d_col;
+        sa.col_stride = plan.stride;
+        sa.strip = 0;
+        sa.item0 = 0;
+        sa.segs = ctx->d_segs;
+        sa.seg_first = ctx->d_seg_first;
+        sa.level = lv;
+        sa.colmap = ctx->d_seg_colmap + L.off;
+        sa.s.counter = ctx->d_seg_cursor + (size_t)lv * 17 + (size_t)(L.kind < 0 ? 16 : L.kind);
+        if (plan.grid)
+        {
+          sa.s.class_profiles = ctx->d_seg_list + L.off;
+          sa.s.nitems = (unsigned long long)L.count * (unsigned long long)a0.nseq;
+        }
+        else
+        {
+          sa.s.order = ctx->d_seg_order + L.off;
+          sa.s.nitems = L.count;
+        }
+        cudaStream_t st = chain;
+        if (L.kind >= 0)
+        { // a tail: any other side stream, after the previous level's full segments
+          st = ctx->side[next_side];
+          next_side = next_side % (dcpgpu_ctx::NSIDE - 1) + 1;
+          CU(cudaStreamWaitEvent(st, ctx->ev_level[lv - 1], 0));
+        }
+        if ((rc = launch_segment(ctx, L.kind, sa, st))) return rc;
+        if (L.kind < 0) CU(cudaEventRecord(ctx->ev_level[lv], chain));
       }
-      else
-      {
-        sa.s.order = ctx->d_seg_order + L.off;
-        sa.s.nitems = L.count;
-      }
-      cudaStream_t st = chain;
-      if (L.kind >= 0)
-      { // a tail: any other side stream, after the previous level's full segments
-        st = ctx->side[next_side];
-        next_side = next_side % (dcpgpu_ctx::NSIDE - 1) + 1;
-        CU(cudaStreamWaitEvent(st, ctx->ev_level[lv - 1], 0));
-      }
-      int const rc = launch_segment(ctx, L.kind, sa, st);
-      if (rc) return rc;
-      if (L.kind < 0) CU(cudaEventRecord(ctx->ev_level[lv], chain));
     }
   }
   return 0;
@@ -1447,7 +1468,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
-  // profiles of more than 256 nodes: segment by segment if the boundary columns fit, else uniform strips
+  // profiles of more than 256 nodes: segment by segment (uniform strips only when segments are switched off)
   SegPlan seg;
   bool seg_ok = false;
   if (ctx->segments)
@@ -1457,9 +1478,8 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       for (long long i : bucket[(size_t)c]) entries.push_back({pairs[i].profile, i});
     if (!entries.empty())
     {
-      rc = prepare_segments(ctx, false, entries, 1, maxlen, &seg);
-      if (rc != 0 && rc != 1) return rc;
-      seg_ok = rc == 0;
+      if ((rc = prepare_segments(ctx, false, entries, 1, maxlen, &seg))) return rc;
+      seg_ok = true;
     }
   }
   StripPlan plan;
@@ -1585,9 +1605,8 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       for (int p : bucket[(size_t)c]) entries.push_back({p, (long long)p});
     if (!entries.empty())
     {
-      rc = prepare_segments(ctx, true, entries, (size_t)nseq, ctx->maxlen, &seg);
-      if (rc != 0 && rc != 1) return rc;
-      seg_ok = rc == 0;
+      if ((rc = prepare_segments(ctx, true, entries, (size_t)nseq, ctx->maxlen, &seg))) return rc;
+      seg_ok = true;
     }
   }
   StripPlan plan;
