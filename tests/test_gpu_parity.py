@@ -316,3 +316,48 @@ def test_layout_variants_agree(node_pool, monkeypatch):
     for other in results[1:]:
         for a, b in zip(base[:7], other[:7]):
             assert np.array_equal(a, b)
+
+
+def test_bench_workload_sample_matches_compiled_reference(reference, node_pool):
+    """A K-stratified sample of bench.py's own workload (same generators, same seeds): every
+    (profile, read) pair scored by the reference's viterbi.c on the host cores (oracle/_ref,
+    multi-threaded scan loop) and by the GPU -- bit-identical null and alternative costs of the
+    first windows and the same hit count."""
+    import os
+    import bench
+    from deciphon_b200.device import Device
+    from deciphon_b200.dcp_file import Profile
+    seed, nprof_db, R, L = 20261018, 20000, 12, 2000
+    sizes = synth.core_sizes(np.random.default_rng(seed), nprof_db)
+    order = np.argsort(sizes, kind="stable")
+    pick = order[np.linspace(0, len(order) - 1, 240).round().astype(int)]
+    reads = bench.make_reads(seed, 0, R - 1, L, sizes, node_pool)
+    # ... plus one read with the consensus of a sampled profile, the way make_reads embeds them
+    rng = np.random.default_rng(seed + 1)
+    q = int(pick[150])
+    cons = synth.consensus_dna(node_pool, bench.profile_nodes(seed, q, sizes[q], node_pool)[0])[: L - 60]
+    reads.append(synth.fixed_length(rng, synth.mutate(rng, np.concatenate(
+        [synth.random_read(rng, 30), cons, synth.random_read(rng, max(0, L - 30 - len(cons)))]), 0.10), L))
+    dev = Device(0)
+    try:
+        first = dev.pool_add(node_pool.emission, node_pool.trans)
+        rprofs = []
+        for p in pick:
+            ids, bmk = bench.profile_nodes(seed, int(p), sizes[p], node_pool)
+            dev.profile_add(int(sizes[p]), bmk, node_pool.null_emission, node_pool.bg_emission, ids + first)
+            tr, em = node_pool.trans[ids], node_pool.emission[ids]
+            pr = Profile("s%d" % p, 1, "", int(sizes[p]), node_pool.null_emission, node_pool.bg_emission,
+                         np.concatenate([tr, tr[-1:]]), np.concatenate([em, em[-1:]]), bmk)
+            rprofs.append(reference.profile(pr.costs()))
+        dev.set_reads(reads)
+        dev.score_grid(0, len(pick), 0, R)
+        nul, alt = dev.scores_fetch(len(pick) * R)
+        nhits = len(dev.hits_fetch())
+        r = reference.scan(rprofs, reads, True, False, os.cpu_count() or 1, want_scores=True)
+        # the reference scans the first window min(50 K, 100000, L) of each pair, like score_grid
+        assert np.array_equal(_bits(nul), _bits(r["null"].reshape(-1)))
+        assert np.array_equal(_bits(alt), _bits(r["alt"].reshape(-1)))
+        d = r["alt"].reshape(-1) - r["null"].reshape(-1)  # lrt >= 0 <=> alt - null <= 0 (lrt.h:6-9)
+        assert nhits == int(np.count_nonzero((d <= 0) & np.isfinite(d))) and nhits > 0
+    finally:
+        dev.close()
