@@ -44,7 +44,7 @@ def measured_traffic():
     """DRAM bytes of the score pass of one step at the default workload, from the committed ncu
     capture (dram__bytes_read.sum + dram__bytes_write.sum; profiles/README.md).  None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic_v13.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic_v16.json")) as f:
             return float(json.load(f)["score_pass_dram_bytes_per_step"])
     except Exception:
         return None
@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--profiles", type=int, default=20000)
-    ap.add_argument("--reads-per-step", type=int, default=48,
+    ap.add_argument("--reads-per-step", type=int, default=96,
                     help="reads per step PER GPU: a step's batch is this many reads times --gpus, so the work of a "
                          "rank (its profile shard x the batch) stays fixed as GPUs are added (weak scaling)")
     ap.add_argument("--read-len", type=int, default=2000)
@@ -349,7 +349,7 @@ def run_b200(args, rank, local_rank, world):
             peak_src = "fallback: nominal 148 SM x 128 lanes x 1.965 GHz"
         achieved = OPS_PER_CELL * stats["cells"] / (stats["score_ms"] * 1e-3) / 1e12
         # DRAM bytes of one step's score pass, ncu capture of this workload (default sizes, one GPU)
-        traffic_bytes = measured_traffic() if (world == 1 and args.profiles == 20000 and args.reads_per_step == 48
+        traffic_bytes = measured_traffic() if (world == 1 and args.profiles == 20000 and args.reads_per_step == 96
                                                and args.read_len == 2000) else None
         line = {
             "metric": "GCUPS (nt x node DP cells/s), Pfam-scale scan", "value": gcups, "unit": "GCUPS",

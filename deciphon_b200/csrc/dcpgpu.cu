@@ -1824,6 +1824,9 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
         all += f;
       }
       need = std::max(need, std::min(all, budget));
+      // a trace that large is a burst of hits and bursts come in all sizes: take the whole budget
+      // once instead of growing (and re-allocating tens of GB) burst after burst
+      if (need > ctx->dump_cap && need > (size_t(1) << 28)) need = std::max(need, budget);
       if (need > ctx->dump_cap)
       {
         if (ctx->d_dump) CU(cudaFree(ctx->d_dump));
