@@ -1311,7 +1311,7 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   // Profiles the strip kernels run are also stored as segments: 256 nodes each in the Q = 8
   // full-warp layout, the tail in the layout a profile of its size would get (strip_kernel.cuh).
   int seg_first = -1, seg_count = 0;
-  if (ctx->segments && d.W > 1 && d.Q <= MAXQ_REG)
+  if (ctx->segments && d.W > 1 && d.W <= 8 && d.Q <= MAXQ_REG) // exactly the strip classes 9..20
   {
     seg_first = (int)ctx->h_segs.size();
     for (int k0 = 0; k0 < K; k0 += 256)
