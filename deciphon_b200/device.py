@@ -145,7 +145,8 @@ class Device:
         return nul, alt
 
     def score_grid(self, prof0: int, prof1: int, seq0: int, seq1: int, multi_hits=True, hmmer3_compat=False):
-        """Asynchronous: first window of every seq in [seq0,seq1) x every profile in [prof0,prof1)."""
+        """First window of every seq in [seq0,seq1) x every profile in [prof0,prof1).  Asynchronous on
+        the context's stream unless profiles of more than 256 nodes are present."""
         self._check(lib.dcpgpu_score_grid(self._h, prof0, prof1, seq0, seq1, flags_of(multi_hits, hmmer3_compat)))
 
     def scores_fetch(self, n: int):
