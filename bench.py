@@ -62,7 +62,7 @@ def parse_args():
                          "rank (its profile shard x the batch) stays fixed as GPUs are added (weak scaling)")
     ap.add_argument("--read-len", type=int, default=2000)
     ap.add_argument("--seed", type=int, default=20261018)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline leg")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline leg (and cap of a reference-arm step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -166,7 +166,7 @@ def run_reference(args, rank):
         return
     pool = synth.NodePool()
     sizes = synth.core_sizes(np.random.default_rng(args.seed), args.profiles)
-    per_step = max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = min(max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))), args.cpu_seconds)
     first = cpu_scan_sample(args, sizes, pool, per_step)
     ref, profs, nreads = first["ref"], first["profs"], first["nreads"]
     times, cells = [], 0.0
