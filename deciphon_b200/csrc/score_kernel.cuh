@@ -335,13 +335,28 @@ __device__ __forceinline__ float d_lazy(Lane<Q> const &s, float (&D)[Q], bool he
   return din;
 }
 
+// min over this lane's nodes of min(M, D): two interleaved chains instead of one (the value
+// feeds E -> B -> P of the next row, the longest dependency of the row's tail)
+template <int Q>
+__device__ __forceinline__ float e_lane(float const (&M)[Q], float const (&D)[Q])
+{
+  float a = fminf(M[0], D[0]);
+  if constexpr (Q == 1) return a;
+  float b = fminf(M[1], D[1]);
+#pragma unroll
+  for (int q = 2; q + 1 < Q; q += 2)
+  {
+    a = min3(a, M[q], D[q]);
+    b = min3(b, M[q + 1], D[q + 1]);
+  }
+  if constexpr ((Q & 1) != 0 && Q > 1) a = min3(a, M[Q - 1], D[Q - 1]);
+  return fminf(a, b);
+}
+
 template <int Q>
 __device__ __forceinline__ float e_partial(float const (&M)[Q], float const (&D)[Q])
 {
-  float e = fminf(M[0], D[0]);
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    e = min3(e, M[q], D[q]);
+  float const e = e_lane<Q>(M, D);
   return warp_min_nonneg(e);
 }
 
@@ -547,10 +562,10 @@ __device__ __forceinline__ void dp_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[Q
   }
 
   // P(l), Q(l) into the slot that held row l-5
-  s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
+  s.P[J][0] = fminf(min3(mprev + s.MM[0], iprev + s.IM[0], dprev + s.DM[0]), B + s.BM[0]); // B last: it arrives last
 #pragma unroll
   for (int q = 1; q < Q; ++q)
-    s.P[J][q] = fminf(min3(B + s.BM[q], M[q - 1] + s.MM[q], I[q - 1] + s.IM[q]), D[q - 1] + s.DM[q]);
+    s.P[J][q] = fminf(min3(M[q - 1] + s.MM[q], I[q - 1] + s.IM[q], D[q - 1] + s.DM[q]), B + s.BM[q]);
 #pragma unroll
   for (int q = 0; q < Q; ++q)
     s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);

@@ -112,10 +112,7 @@ __device__ __forceinline__ void sub_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[
   float const dprev = d_lazy_seg<Q, SEG>(s, D);
 
   // E(l) = min_k min(M_k, D_k) over the pair's own lanes (viterbi.c:540-558)
-  float e = fminf(M[0], D[0]);
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    e = min3(e, M[q], D[q]);
+  float e = e_lane<Q>(M, D);
   E = seg_min<SEG>(e);
 
   // special states: x is N(l) on segment lane 0, J(l) on 1, C(l) on 2, R(l) on 3
@@ -146,10 +143,10 @@ __device__ __forceinline__ void sub_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)[
   }
 
   // P(l), Q(l) into the slot that held row l-5
-  s.P[J][0] = fminf(min3(B + s.BM[0], mprev + s.MM[0], iprev + s.IM[0]), dprev + s.DM[0]);
+  s.P[J][0] = fminf(min3(mprev + s.MM[0], iprev + s.IM[0], dprev + s.DM[0]), B + s.BM[0]); // B last: it arrives last
 #pragma unroll
   for (int q = 1; q < Q; ++q)
-    s.P[J][q] = fminf(min3(B + s.BM[q], M[q - 1] + s.MM[q], I[q - 1] + s.IM[q]), D[q - 1] + s.DM[q]);
+    s.P[J][q] = fminf(min3(M[q - 1] + s.MM[q], I[q - 1] + s.IM[q], D[q - 1] + s.DM[q]), B + s.BM[q]);
 #pragma unroll
   for (int q = 0; q < Q; ++q)
     s.Qv[J][q] = fminf(I[q] + s.II[q], M[q] + s.MI[q]);

@@ -98,10 +98,7 @@ __device__ __forceinline__ void tail_row(Lane<Q> &s, float (&Mp)[Q], float (&Ip)
   }
   float const dprev = d_lazy_seg_in<Q, SEG>(s, D, head, b.z);
 
-  float e = fminf(M[0], D[0]);
-#pragma unroll
-  for (int q = 1; q < Q; ++q)
-    e = min3(e, M[q], D[q]);
+  float e = e_lane<Q>(M, D);
   e = fminf(seg_min<SEG>(e), b.w); // E(l) of the whole row
   E = e;
 
