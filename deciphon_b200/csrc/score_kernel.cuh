@@ -11,7 +11,11 @@
 // which is value-exact (bit-identical) with the reference because fp32 rounding is
 // monotone: min_i((s_i + tau_i) + e) == (min_i (s_i + tau_i)) + e.
 //
-// Mapping: W WARPS PER PAIR (W = 1 for K <= 256, 2/4/8 up to K = 2048).  The K nodes are
+// This file is the DP row and the exact kernel, W WARPS PER PAIR (W = 1 for K <= 256, 2/4/8 up
+// to K = 2048).  The score pass uses it as is for 128 < K <= 256; smaller profiles share a warp
+// (sub_kernel.cuh), larger ones are scored as speculative strips (strip_kernel.cuh,
+// tail_kernel.cuh) and come back here -- W = 2/4/8 -- only when the speculation fails, and for
+// the trace pass's value dump (DUMP).  The K nodes are
 // striped across the VL = 32*W "virtual lanes" like the reference stripes them across SIMD
 // lanes (viterbi.c:220-221): vl = k / Q, q = k % Q, Q <= 8.  Per lane everything lives in
 // registers:
@@ -73,7 +77,7 @@ struct ScoreArgs
 };
 
 // Layout of one traced pair's value dump: rows l = 1..L (row 0 is all +INF except B = SB).
-//   M, I, D : [L][Kpad] each, node k at column k (= vl*Q + q)
+//   M, I, D : [L][Kpad] each, node k at column layout_pos(k) (the lane-chunked order of layout.cuh)
 //   xs      : [L][8] = N, B, J, E, C
 // Dumped DP values of one pair: M, I, D as [L][Kpad] with node k of a row at layout_pos(k)
 // (the order the lanes hold them, so a row is written with full-width stores), then
