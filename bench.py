@@ -127,38 +127,86 @@ class ClockSampler(threading.Thread):
 
 # ---- reference / CPU leg --------------------------------------------------------------------
 
-def cpu_scan_sample(args, sizes, pool, target_seconds, want_line=False):
-    """The reference's viterbi.c/trellis.c (oracle/_ref) driven like its scan loop on all host
-    cores over a bounded, seed-fixed, K-stratified sample of the same workload."""
-    from oracle.oracle import Reference
-    ref = Reference()
-    cores = os.cpu_count() or 1
-    nprof = max(cores, 32)
+def balanced_sample(sizes, cores, per_thread, seed):
+    """K-stratified sample of per_thread x cores profiles, ordered so that the reference's
+    contiguous count partitions (scan.c:188-208, partition_size.c:13-16: cores partitions of
+    per_thread consecutive profiles) carry near-equal sum K -- what partitioning 20,000 profiles
+    by count gives the real scan (1,250 profiles per thread average out), and what a sample of
+    one or two profiles per thread does not."""
+    nprof = per_thread * cores
     order = np.argsort(sizes, kind="stable")
-    pick = order[np.linspace(0, len(order) - 1, nprof).round().astype(int)]
-    rng = np.random.default_rng(args.seed)
-    rng.shuffle(pick)  # contiguous partitions then hold mixed sizes
+    pick = order[np.linspace(0, len(order) - 1, nprof).round().astype(int)][::-1]  # largest first
+    parts = [[] for _ in range(cores)]
+    for r in range(per_thread):  # snake deal: round r hands one profile to every partition
+        row = pick[r * cores:(r + 1) * cores]
+        for j, p in enumerate(row if r % 2 == 0 else row[::-1]):
+            parts[j].append(int(p))
+    rng = np.random.default_rng(seed)
+    for part in parts:
+        rng.shuffle(part)  # mixed sizes inside a partition, like a real database
+    return np.asarray([p for part in parts for p in part], dtype=np.int64)
+
+
+def cpu_scan_sample(args, sizes, pool, target_seconds, simd=None):
+    """The reference's viterbi.c/trellis.c/xtrans.c (oracle/_ref) driven like its scan loop on all
+    host cores over a bounded, seed-fixed, K-stratified sample of the same workload: 32 profiles
+    per thread, balanced by sum K over the count partitions, every window.c window of a pair."""
+    from deciphon_b200.dcp_file import Profile
+    from oracle.oracle import Reference, ref_lib_path
+    if simd:
+        os.environ["DCP_REF_SIMD"] = simd
+    try:
+        ref = Reference(ref_lib_path())
+    finally:
+        os.environ.pop("DCP_REF_SIMD", None)
+    cores = os.cpu_count() or 1
+    per_thread = 32
+    pick = balanced_sample(sizes, cores, per_thread, args.seed)
     profs = []
     for p in pick:
         ids, bmk = profile_nodes(args.seed, int(p), sizes[p], pool)
         tr, em = pool.trans[ids], pool.emission[ids]
-        from deciphon_b200.dcp_file import Profile
         pr = Profile("s%d" % p, 1, "", int(sizes[p]), pool.null_emission, pool.bg_emission,
                      np.concatenate([tr, tr[-1:]]), np.concatenate([em, em[-1:]]), bmk)
         profs.append(ref.profile(pr.costs()))
     probe_reads = make_reads(args.seed, 0, 2, args.read_len, sizes, pool)
+    ref.scan(profs, probe_reads, True, False, cores)  # first touch of the tables
     t = ref.scan(profs, probe_reads, True, False, cores)
     rate = t["cells"] / max(t["seconds"], 1e-9)
     per_read = t["cells"] / 2
     nreads = int(max(2, min(4000, round(target_seconds * rate / per_read))))
     reads = make_reads(args.seed, 0, nreads, args.read_len, sizes, pool)
     r = ref.scan(profs, reads, True, False, cores)
-    sample = (f"{nprof} K-stratified profiles (sum K = {int(sizes[pick].sum())}) x {nreads} reads of "
-              f"{args.read_len} nt, null+alt Viterbi per window, trellis+unzip for lrt>=0 ({r['hits']} hits), "
-              f"{r['cells']:.3e} cells in {r['seconds']:.2f} s, {os.path.basename(ref.path)}")
-    return {"gcups": r["cells"] / r["seconds"] / 1e9, "reads_per_s": None, "cores": cores, "sample": sample,
+    ts = r["thread_seconds"]
+    gcups = r["cells"] / r["seconds"] / 1e9
+    sample = (f"{len(pick)} K-stratified profiles = {per_thread} per thread x {cores} threads, sum-K-balanced count "
+              f"partitions (sum K = {int(sizes[pick].sum())}) x {nreads} reads of {args.read_len} nt, every window.c "
+              f"window, xtrans + null + alt Viterbi per window, trellis+unzip for lrt>=0 ({r['hits']} hits), "
+              f"{r['cells']:.3e} cells in {r['seconds']:.2f} s; per-thread busy {ts.min():.2f}..{ts.max():.2f} s, "
+              f"parallel efficiency {r['parallel_efficiency']:.3f}, {gcups / cores:.4f} GCUPS per core; "
+              f"{os.path.basename(ref.path)}")
+    return {"gcups": gcups, "reads_per_s": None, "cores": cores, "sample": sample,
             "seconds": r["seconds"], "cells": r["cells"], "profs": profs, "ref": ref, "nreads": nreads,
-            "sumK_sample": int(sizes[pick].sum())}
+            "sumK_sample": int(sizes[pick].sum()), "parallel_efficiency": r["parallel_efficiency"],
+            "reads": reads}
+
+
+def cpu_baseline_record(args, sizes, pool):
+    """cpu_baseline of the measured arm: the widest SIMD build this host runs, plus the reference
+    Makefile's default level (-mavx2, c-core/Makefile:10-12) on a third of the sample."""
+    c = cpu_scan_sample(args, sizes, pool, args.cpu_seconds)
+    rec = {"value": c["gcups"], "unit": "GCUPS", "cores": c["cores"], "kind": "reference", "sample": c["sample"],
+           "parallel_efficiency": c["parallel_efficiency"]}
+    wide = os.path.basename(c["ref"].path)
+    c.clear()
+    if "avx512" in wide:
+        try:
+            d = cpu_scan_sample(args, sizes, pool, max(3.0, args.cpu_seconds / 3), simd="avx2")
+            rec["makefile_default_avx2"] = {"value": d["gcups"], "unit": "GCUPS", "cores": d["cores"],
+                                            "parallel_efficiency": d["parallel_efficiency"], "sample": d["sample"]}
+        except Exception as e:
+            rec["makefile_default_avx2"] = {"value": None, "sample": f"unavailable: {e}"}
+    return rec
 
 
 def run_reference(args, rank):
@@ -169,13 +217,14 @@ def run_reference(args, rank):
     per_step = min(max(2.0, min(20.0, 120.0 / max(1, args.steps + args.warmup))), args.cpu_seconds)
     first = cpu_scan_sample(args, sizes, pool, per_step)
     ref, profs, nreads = first["ref"], first["profs"], first["nreads"]
-    times, cells = [], 0.0
+    times, cells, effs = [], 0.0, []
     for i in range(args.warmup + args.steps):
         reads = make_reads(args.seed, i * nreads, nreads, args.read_len, sizes, pool)
         r = ref.scan(profs, reads, True, False, first["cores"])
         if i >= args.warmup:
             times.append(r["seconds"])
             cells += r["cells"]
+            effs.append(r["parallel_efficiency"])
     gcups = cells / sum(times) / 1e9
     full_cells_per_read = float(np.minimum(sizes * 50, args.read_len).astype(np.float64) @ sizes)
     line = {
@@ -186,6 +235,7 @@ def run_reference(args, rank):
         "config": workload_config(args, sizes, None),
         "reads_per_s": gcups * 1e9 / full_cells_per_read,
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": first["cores"], "kind": "reference",
+                         "parallel_efficiency": float(np.mean(effs)),
                          "sample": first["sample"] + f"; each step = a fresh batch of {nreads} reads on the same profiles"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -219,7 +269,7 @@ def run_b200(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (deciphon_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line unless the caller asks for more
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -372,9 +422,7 @@ def run_b200(args, rank, local_rank, world):
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                c = cpu_scan_sample(args, sizes, pool, args.cpu_seconds)
-                line["cpu_baseline"] = {"value": c["gcups"], "unit": "GCUPS", "cores": c["cores"], "kind": "reference",
-                                        "sample": c["sample"]}
+                line["cpu_baseline"] = cpu_baseline_record(args, sizes, pool)
             except Exception as e:  # the checker is optional for the measured arm
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"unavailable: {e}"}

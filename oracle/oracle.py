@@ -153,8 +153,24 @@ def ref_lib_path() -> str | None:
     return None
 
 
+def ref_xtrans(window_lens, multi_hits: bool, hmmer3_compat: bool) -> np.ndarray:
+    """The 13 special-transition costs the REFERENCE loads for windows of the given lengths:
+    its own xtrans.c (oracle/_ref/libdcpref_xtrans.so), called like thread.c:112 with
+    seq_size = max(L / 3, 1).  Returns float32 [n][13] in viterbi.h:4-19 order."""
+    path = os.path.join(HERE, "_ref", "libdcpref_xtrans.so")
+    if not os.path.exists(path) and os.path.isdir("/root/reference/c-core"):
+        build()
+    lib = C.CDLL(path)
+    lens = np.atleast_1d(np.asarray(window_lens, dtype=np.int64))
+    ss = np.ascontiguousarray(np.maximum(lens // 3, 1).astype(np.int32))
+    out = np.empty((len(ss), 13), dtype=np.float32)
+    lib.ref_xtrans_many.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.ref_xtrans_many(len(ss), ss.ctypes.data, int(multi_hits), int(hmmer3_compat), out.ctypes.data)
+    return out
+
+
 class Reference:
-    """The reference's own viterbi.c/trellis.c (oracle/_ref)."""
+    """The reference's own viterbi.c/trellis.c/xtrans.c (oracle/_ref)."""
 
     def __init__(self, path: str | None = None):
         path = path or ref_lib_path()
@@ -177,7 +193,7 @@ class Reference:
         L.ref_path.argtypes = [C.c_void_p, u8p, C.c_int, u16p, u8p, C.c_int, C.c_void_p, C.c_void_p]
         L.ref_scan.argtypes = [C.c_int, C.POINTER(C.c_void_p), C.c_int, u8p, i64p, C.c_int, C.c_int,
                                C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_double),
-                               C.POINTER(C.c_int64)]
+                               C.POINTER(C.c_int64), C.c_void_p]
         L.ref_scan.restype = C.c_double
         L.ref_num_lanes.restype = C.c_int
         self.lanes = L.ref_num_lanes()
@@ -204,9 +220,13 @@ class Reference:
             nul = np.zeros((n, len(reads)), dtype=np.float32)
             alt = np.zeros((n, len(reads)), dtype=np.float32)
             pn, pa = nul.ctypes.data, alt.ctypes.data
+        nthreads = max(1, min(int(nthreads), n))
+        tsec = np.zeros(nthreads, dtype=np.float64)
         sec = self.lib.ref_scan(n, arr, len(reads), x, off, int(multi_hits), int(hmmer3_compat),
-                                int(nthreads), pn, pa, C.byref(cells), C.byref(hits))
-        return {"seconds": sec, "cells": cells.value, "hits": hits.value, "null": nul, "alt": alt}
+                                nthreads, pn, pa, C.byref(cells), C.byref(hits), tsec.ctypes.data)
+        return {"seconds": sec, "cells": cells.value, "hits": hits.value, "null": nul, "alt": alt,
+                "thread_seconds": tsec, "threads": nthreads,
+                "parallel_efficiency": float(tsec.sum() / (nthreads * max(sec, 1e-12)))}
 
 
 class RefProfile:

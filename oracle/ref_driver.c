@@ -8,12 +8,14 @@
  * the reference is copied.  Used to (a) validate oracle/dcp_oracle.c and the CUDA
  * path bit-for-bit and (b) time the reference CPU scan (bench.py --impl reference).
  *
- * The special transitions come from oracle/dcp_oracle.c:orc_xtrans because
- * c-core/xtrans.c needs third-party imm headers and cannot be built here.
+ * The special transitions of ref_scan come from the reference's own c-core/xtrans.c
+ * (compiled with two-macro stand-ins for imm_lprob.h / imm_dump.h, oracle/ref_shim/);
+ * ref_set_xtrans still lets a test load any 13 costs.
  */
 #include "imm_path.h"
 #include "trellis.h"
 #include "viterbi.h"
+#include "xtrans.h"
 #include <math.h>
 #include <omp.h>
 #include <stdint.h>
@@ -24,7 +26,6 @@
 #define NCODES 1364
 enum { C_BM, C_MM, C_MI, C_MD, C_IM, C_II, C_DM, C_DD, C_N };
 
-void orc_xtrans(int window_len, int multi_hits, int hmmer3_compat, float out[13]);
 int orc_window_next(int st[4], int seq_len, int core_size);
 int orc_hit_extent(int nsteps, uint16_t const *state_ids, uint8_t const *sizes, int *hit_start,
                    int *hit_stop, int *begin, int *end);
@@ -149,11 +150,14 @@ int ref_path(struct ref_profile *p, uint8_t const *x, int L, uint16_t *state_ids
  *
  * profs[nprof]; reads are symbols 0..3, concatenated, read r = x[off[r]..off[r+1]).
  * out_null/out_alt (optional) receive the FIRST window's costs per (profile, read).
+ * thread_seconds (optional, nthreads entries) receives each partition's busy time, so the
+ * caller can report the parallel efficiency of the count partitioning.
  * Returns wall seconds; *cells = sum of L*K over windows, *nhits = windows with lrt >= 0.
  */
 double ref_scan(int nprof, struct ref_profile **profs, int nreads, uint8_t const *x,
                 int64_t const *off, int multi_hits, int hmmer3_compat, int nthreads,
-                float *out_null, float *out_alt, double *cells, int64_t *nhits)
+                float *out_null, float *out_alt, double *cells, int64_t *nhits,
+                double *thread_seconds)
 {
   if (nthreads > nprof) nthreads = nprof;
   if (nthreads < 1) nthreads = 1;
@@ -168,6 +172,8 @@ double ref_scan(int nprof, struct ref_profile **profs, int nreads, uint8_t const
     for (int i = 0; i < part; ++i)
       start += (int)(((long)(nprof - i > 0 ? nprof - i : 0) + nthreads - 1) / nthreads);
     int size = (int)(((long)(nprof - part > 0 ? nprof - part : 0) + nthreads - 1) / nthreads);
+    struct timespec p0, p1;
+    clock_gettime(CLOCK_MONOTONIC, &p0);
     int cap = 0;
     uint16_t *ids = NULL;
     uint8_t *szs = NULL;
@@ -182,9 +188,10 @@ double ref_scan(int nprof, struct ref_profile **profs, int nreads, uint8_t const
         {
           int L = st[1] - st[0];
           uint8_t const *w = x + off[r] + st[0];
-          float xt[13];
-          orc_xtrans(L, multi_hits, hmmer3_compat, xt);
-          set_xtrans(p->v, xt);
+          struct xtrans xt; /* work_reset(work, max(L / 3, 1)), c-core/thread.c:112 */
+          xtrans_init(&xt);
+          xtrans_setup(&xt, multi_hits != 0, hmmer3_compat != 0, L / 3 > 1 ? L / 3 : 1);
+          xtrans_setup_viterbi(&xt, p->v);
           float nul = ref_null(p, w, L);
           float alt = ref_cost(p, w, L);
           tot_cells += (double)L * p->K;
@@ -208,6 +215,9 @@ double ref_scan(int nprof, struct ref_profile **profs, int nreads, uint8_t const
     }
     free(ids);
     free(szs);
+    clock_gettime(CLOCK_MONOTONIC, &p1);
+    if (thread_seconds)
+      thread_seconds[part] = (double)(p1.tv_sec - p0.tv_sec) + 1e-9 * (double)(p1.tv_nsec - p0.tv_nsec);
   }
   clock_gettime(CLOCK_MONOTONIC, &t1);
   if (cells) *cells = tot_cells;

@@ -35,6 +35,27 @@ def test_xtrans_matches_oracle(oracle):
                 assert device.xtrans(L, mh, h3).tobytes() == oracle.xtrans(L, mh, h3).tobytes()
 
 
+def test_xtrans_matches_reference_xtrans_c(oracle):
+    """dcpgpu_xtrans and the oracle against the REFERENCE's own xtrans.c (compiled where it lies
+    into oracle/_ref/libdcpref_xtrans.so), bit for bit, every window length 1..100000 (the
+    maximum window, window.c:7) x the four multi_hits x hmmer3_compat combinations."""
+    from deciphon_b200 import device
+    from oracle.oracle import ref_xtrans
+    lens = np.arange(1, 100001)
+    for mh in (False, True):
+        for h3 in (False, True):
+            want = ref_xtrans(lens, mh, h3)
+            # costs depend on L only through max(L / 3, 1): one device/oracle call per distinct value
+            first = np.unique(np.maximum(lens // 3, 1), return_index=True)[1]
+            for i in first:
+                L = int(lens[i])
+                assert device.xtrans(L, mh, h3).tobytes() == want[i].tobytes(), (L, mh, h3)
+                assert oracle.xtrans(L, mh, h3).tobytes() == want[i].tobytes(), (L, mh, h3)
+            # and the expansion back to every length is the reference's
+            same = np.maximum(lens // 3, 1)
+            assert np.array_equal(want.view(np.uint32), want[first][np.searchsorted(same[first], same)].view(np.uint32))
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
