@@ -10,7 +10,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdcpgpu.so")
+# DCPGPU_LIB: developer switch for A/B builds of the CUDA library (scripts/quick_perf.py); the
+# product always loads the in-tree deciphon_b200/libdcpgpu.so
+LIB_PATH = os.environ.get("DCPGPU_LIB") or os.path.join(HERE, "libdcpgpu.so")
 
 # every symbol include/dcpgpu.h declares: (name, restype, argtypes)
 _vp, _i32, _i64, _u32, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_float

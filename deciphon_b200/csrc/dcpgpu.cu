@@ -8,10 +8,8 @@
 #include "../../include/dcpgpu.h"
 #include "generic_kernel.cuh"
 #include "layout.cuh"
-#include "score_kernel.cuh"
-#include "strip_kernel.cuh"
-#include "sub_kernel.cuh"
-#include "tail_kernel.cuh"
+#include "kernels.h"
+#include "row_kernel.cuh"
 #include "trace_argmin.cuh"
 #include "trace_walk.cuh"
 
@@ -75,7 +73,6 @@ struct dcpgpu_ctx
   ProfileDesc *d_segs = nullptr;
   int *d_seg_first = nullptr;
   size_t d_segs_cap = 0, d_seg_first_cap = 0;
-  bool segments = true; // DCPGPU_SEGMENTS=0: uniform strips of the whole-profile layout (A/B switch)
   static constexpr int MAXSEG = 8;
   cudaEvent_t ev_level[MAXSEG] = {};
   unsigned long long *d_seg_cursor = nullptr; // [MAXSEG * 17] work cursors of the segment launches
@@ -91,6 +88,7 @@ struct dcpgpu_ctx
   // reads
   uint32_t *d_words = nullptr;
   long long nwords = 0;
+  uint16_t *d_hist = nullptr; // ten-bit history of every position of the packed stream (row_kernel.cuh)
   long long *d_seq_word = nullptr;
   int *d_seq_len = nullptr;
   std::vector<int> h_seq_len;
@@ -459,193 +457,30 @@ int kernel_class(dcpgpu_ctx const *ctx, int profile)
   return 0;
 }
 
-template <int Q, int W, bool DUMP = false>
-int launch_reg(dcpgpu_ctx *ctx, ScoreArgs const &a)
-{
-  constexpr int T = ScoreCfg<W>::THREADS, G = ScoreCfg<W>::GROUPS;
-  constexpr size_t SMEM = score_smem_bytes<Q, W>();
-  static bool configured = false;
-  if (!configured)
-  {
-    CU(cudaFuncSetAttribute(score_reg_kernel<Q, W, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    configured = true;
-  }
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W, DUMP>, T, SMEM));
-  if (per_sm < 1) per_sm = 1;
-  unsigned long long const want = (a.nitems + G - 1) / G;
-  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  score_reg_kernel<Q, W, DUMP><<<grid, T, SMEM, launch_stream(ctx)>>>(a);
-  CU(cudaGetLastError());
-  ctx->launches += 1;
-  return 0;
-}
-
-template <int Q, int G, bool DUMP>
-int launch_sub(dcpgpu_ctx *ctx, ScoreArgs const &a)
-{
-  constexpr int T = 32 * SUB_GROUPS;
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_sub_kernel<Q, G, DUMP>, T, 0));
-  if (per_sm < 1) per_sm = 1;
-  unsigned long long const want = (a.nitems + G * SUB_GROUPS - 1) / (G * SUB_GROUPS);
-  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  score_sub_kernel<Q, G, DUMP><<<grid, T, 0, launch_stream(ctx)>>>(a);
-  CU(cudaGetLastError());
-  ctx->launches += 1;
-  return 0;
-}
-
+// kernel class -> launcher (kernels.h); every launch lands on launch_stream(ctx)
 template <bool DUMP>
 int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 {
-  switch (cls)
+  cudaStream_t const st = launch_stream(ctx);
+  cudaError_t e;
+  if (cls >= 1 && cls <= 8 || cls >= 21 && cls <= 32)
   {
-  case 21: return launch_sub<5, 2, DUMP>(ctx, a);
-  case 22: return launch_sub<6, 2, DUMP>(ctx, a);
-  case 23: return launch_sub<7, 2, DUMP>(ctx, a);
-  case 24: return launch_sub<8, 2, DUMP>(ctx, a);
-  case 25: return launch_sub<5, 4, DUMP>(ctx, a);
-  case 26: return launch_sub<6, 4, DUMP>(ctx, a);
-  case 27: return launch_sub<7, 4, DUMP>(ctx, a);
-  case 28: return launch_sub<8, 4, DUMP>(ctx, a);
-  case 29: return launch_sub<5, 8, DUMP>(ctx, a);
-  case 30: return launch_sub<6, 8, DUMP>(ctx, a);
-  case 31: return launch_sub<7, 8, DUMP>(ctx, a);
-  case 32: return launch_sub<8, 8, DUMP>(ctx, a);
-  case 1: return launch_reg<1, 1, DUMP>(ctx, a);
-  case 2: return launch_reg<2, 1, DUMP>(ctx, a);
-  case 3: return launch_reg<3, 1, DUMP>(ctx, a);
-  case 4: return launch_reg<4, 1, DUMP>(ctx, a);
-  case 5: return launch_reg<5, 1, DUMP>(ctx, a);
-  case 6: return launch_reg<6, 1, DUMP>(ctx, a);
-  case 7: return launch_reg<7, 1, DUMP>(ctx, a);
-  case 8: return launch_reg<8, 1, DUMP>(ctx, a);
-  case 9: return launch_reg<5, 2, DUMP>(ctx, a);
-  case 10: return launch_reg<6, 2, DUMP>(ctx, a);
-  case 11: return launch_reg<7, 2, DUMP>(ctx, a);
-  case 12: return launch_reg<8, 2, DUMP>(ctx, a);
-  case 13: return launch_reg<5, 4, DUMP>(ctx, a);
-  case 14: return launch_reg<6, 4, DUMP>(ctx, a);
-  case 15: return launch_reg<7, 4, DUMP>(ctx, a);
-  case 16: return launch_reg<8, 4, DUMP>(ctx, a);
-  case 17: return launch_reg<5, 8, DUMP>(ctx, a);
-  case 18: return launch_reg<6, 8, DUMP>(ctx, a);
-  case 19: return launch_reg<7, 8, DUMP>(ctx, a);
-  case 20: return launch_reg<8, 8, DUMP>(ctx, a);
-  default: return fail(ctx, DCPGPU_EINVAL, "bad kernel class");
+    StripArgs sa{};
+    sa.s = a;
+    int const Q = cls <= 8 ? cls : 5 + (cls - 21) % 4;
+    int const SEG = cls <= 8 ? 32 : cls <= 24 ? 16 : cls <= 28 ? 8 : 4;
+    e = launch_row(Q, SEG, ROW_WHOLE, DUMP, sa, ctx->sm_count, st);
   }
-}
-
-int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a) { return launch_class_t<false>(ctx, cls, a); }
-
-// f(Q, W) for a strip class 9..20 (W = 2/4/8 x Q = 5..8)
-template <class F>
-int strip_dispatch(dcpgpu_ctx *ctx, int cls, F &&f)
-{
-#define DCP_SC(c, Q_, W_) \
-  case c: return f(std::integral_constant<int, Q_>{}, std::integral_constant<int, W_>{});
-  switch (cls)
-  {
-    DCP_SC(9, 5, 2) DCP_SC(10, 6, 2) DCP_SC(11, 7, 2) DCP_SC(12, 8, 2)
-    DCP_SC(13, 5, 4) DCP_SC(14, 6, 4) DCP_SC(15, 7, 4) DCP_SC(16, 8, 4)
-    DCP_SC(17, 5, 8) DCP_SC(18, 6, 8) DCP_SC(19, 7, 8) DCP_SC(20, 8, 8)
-  default: return fail(ctx, DCPGPU_EINVAL, "bad strip class");
-  }
-#undef DCP_SC
-}
-
-template <int Q, int W, bool FIRST, bool LAST>
-int launch_lstrip_one(dcpgpu_ctx *ctx, StripArgs const &a, unsigned long long count, cudaStream_t st)
-{
-  int per_sm = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_lstrip_kernel<Q, W, FIRST, LAST>, 32 * LSTRIP_WARPS, 0));
-  if (per_sm < 1) per_sm = 1;
-  unsigned long long const want = (count + LSTRIP_WARPS - 1) / LSTRIP_WARPS;
-  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-  CU(cudaMemsetAsync(a.s.counter, 0, sizeof(unsigned long long), st));
-  score_lstrip_kernel<Q, W, FIRST, LAST><<<grid, 32 * LSTRIP_WARPS, 0, st>>>(a);
-  CU(cudaGetLastError());
+  else if (cls >= 9 && cls <= 20)
+    e = launch_reg_multi(5 + (cls - 9) % 4, cls <= 12 ? 2 : cls <= 16 ? 4 : 8, DUMP, a, ctx->sm_count, st);
+  else
+    return fail(ctx, DCPGPU_EINVAL, "bad kernel class");
+  CU(e);
   ctx->launches += 1;
   return 0;
 }
 
-// Strips 0..W-1 of the items [item0, item0 + count) of one class, one launch each, in stream order.
-template <int Q, int W>
-int launch_lstrips(dcpgpu_ctx *ctx, StripArgs a, unsigned long long item0, unsigned long long count, cudaStream_t st)
-{
-  a.item0 = item0;
-  a.s.nitems = item0 + count;
-  int rc;
-  for (int w = 0; w < W; ++w)
-  {
-    a.strip = w;
-    if (w == 0) rc = launch_lstrip_one<Q, W, true, false>(ctx, a, count, st);
-    else if (w == W - 1) rc = launch_lstrip_one<Q, W, false, true>(ctx, a, count, st);
-    else if constexpr (W > 2) rc = launch_lstrip_one<Q, W, false, false>(ctx, a, count, st);
-    else rc = DCPGPU_ESTATE;
-    if (rc) return rc;
-  }
-  return 0;
-}
-
-// Boundary-column memory of a pass: `count[c]` items per strip class, windows up to maxlen.
-// If everything fits the budget every class gets its own region and the classes run
-// concurrently; otherwise the classes take turns with the whole buffer, in chunks.
-struct StripPlan
-{
-  size_t stride = 0;          // Mails per item
-  size_t region[NCLASS] = {}; // first Mail of the class's region
-  size_t chunk = 0;           // items per chunk when the classes take turns (0: all at once)
-};
-
-int plan_strips(dcpgpu_ctx *ctx, unsigned long long const *count, int maxlen, StripPlan *plan)
-{
-  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
-  size_t total = 0;
-  for (int c = 9; c <= 20; ++c)
-  {
-    plan->region[c] = total * plan->stride;
-    total += (size_t)count[c];
-  }
-  if (!total) return 0;
-  size_t fr = 0, tot = 0;
-  CU(cudaMemGetInfo(&fr, &tot));
-  size_t const have = ctx->col_cap * sizeof(Mail);
-  size_t const budget = std::min<size_t>((fr + have) / 2, ctx->col_budget) / (plan->stride * sizeof(Mail));
-  size_t items = total;
-  if (total > budget)
-  {
-    plan->chunk = items = std::max<size_t>(budget, 1);
-    for (int c = 9; c <= 20; ++c) plan->region[c] = 0;
-  }
-  if (items * plan->stride <= ctx->col_cap) return 0;
-  if (ctx->d_col) CU(cudaFree(ctx->d_col));
-  ctx->d_col = nullptr;
-  ctx->col_cap = 0;
-  CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_col), items * plan->stride * sizeof(Mail)));
-  ctx->col_cap = items * plan->stride;
-  return 0;
-}
-
-// classes 9..20: speculative strips first, the exact multi-warp kernel for the pairs that fail
-int launch_strip_class(dcpgpu_ctx *ctx, int cls, StripArgs a, StripPlan const &plan)
-{
-  return strip_dispatch(ctx, cls, [&](auto q, auto w) {
-    constexpr int Q = decltype(q)::value, W = decltype(w)::value;
-    a.col = ctx->d_col + plan.region[cls];
-    a.col_stride = plan.stride;
-    unsigned long long const n = a.s.nitems;
-    if (!plan.chunk) return launch_lstrips<Q, W>(ctx, a, 0, n, launch_stream(ctx));
-    // the classes share one buffer: everything on the main stream, chunk after chunk
-    for (unsigned long long i0 = 0; i0 < n; i0 += plan.chunk)
-    {
-      int const rc = launch_lstrips<Q, W>(ctx, a, i0, std::min<unsigned long long>(plan.chunk, n - i0), ctx->stream);
-      if (rc) return rc;
-    }
-    return 0;
-  });
-}
+int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a) { return launch_class_t<false>(ctx, cls, a); }
 
 // ---- segmented profiles: level-by-level launches (strip_kernel.cuh, tail_kernel.cuh) ----------
 // kind of a segment launch: -2 = first full segment, -1 = later full segment, 0..15 = tail class
@@ -658,40 +493,14 @@ int tail_class(ProfileDesc const &g)
 
 int launch_segment(dcpgpu_ctx *ctx, int kind, StripArgs const &a, cudaStream_t st)
 {
-  auto go = [&](auto kernel, int per_cta) -> int {
-    int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0));
-    if (per_sm < 1) per_sm = 1;
-    unsigned long long const want = (a.s.nitems + per_cta - 1) / per_cta;
-    unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * ctx->sm_count);
-    kernel<<<grid, 128, 0, st>>>(a);
-    CU(cudaGetLastError());
-    ctx->launches += 1;
-    return 0;
-  };
-  static_assert(LSTRIP_WARPS == 4 && SUB_GROUPS == 4, "128-thread CTAs");
-  switch (kind)
-  {
-  case -2: return go(score_lstrip_kernel<8, 1, true, false>, 4);
-  case -1: return go(score_lstrip_kernel<8, 1, false, false>, 4);
-  case 0: return go(score_lstrip_kernel<5, 1, false, true>, 4);
-  case 1: return go(score_lstrip_kernel<6, 1, false, true>, 4);
-  case 2: return go(score_lstrip_kernel<7, 1, false, true>, 4);
-  case 3: return go(score_lstrip_kernel<8, 1, false, true>, 4);
-  case 4: return go(score_subtail_kernel<5, 2>, 8);
-  case 5: return go(score_subtail_kernel<6, 2>, 8);
-  case 6: return go(score_subtail_kernel<7, 2>, 8);
-  case 7: return go(score_subtail_kernel<8, 2>, 8);
-  case 8: return go(score_subtail_kernel<5, 4>, 16);
-  case 9: return go(score_subtail_kernel<6, 4>, 16);
-  case 10: return go(score_subtail_kernel<7, 4>, 16);
-  case 11: return go(score_subtail_kernel<8, 4>, 16);
-  case 12: return go(score_subtail_kernel<5, 8>, 32);
-  case 13: return go(score_subtail_kernel<6, 8>, 32);
-  case 14: return go(score_subtail_kernel<7, 8>, 32);
-  case 15: return go(score_subtail_kernel<8, 8>, 32);
-  default: return fail(ctx, DCPGPU_EINVAL, "bad segment kind");
-  }
+  cudaError_t e;
+  if (kind == -2) e = launch_row(8, 32, ROW_FIRST, false, a, ctx->sm_count, st);
+  else if (kind == -1) e = launch_row(8, 32, ROW_MID, false, a, ctx->sm_count, st);
+  else if (kind >= 0 && kind < 16) e = launch_row(5 + kind % 4, 32 >> (kind / 4), ROW_LAST, false, a, ctx->sm_count, st);
+  else return fail(ctx, DCPGPU_EINVAL, "bad segment kind");
+  CU(e);
+  ctx->launches += 1;
+  return 0;
 }
 
 struct SegLaunch
@@ -966,9 +775,11 @@ ReadsView reads_view(dcpgpu_ctx const *ctx)
 {
   ReadsView r;
   r.words = ctx->d_words;
+  r.hist = ctx->d_hist;
   r.seq_word = ctx->d_seq_word;
   r.seq_len = ctx->d_seq_len;
   r.nseq = ctx->nseq;
+  r.eight = 8;
   r.nwords = ctx->nwords;
   return r;
 }
@@ -1068,8 +879,6 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   {
     char const *v = std::getenv("DCPGPU_SUBWARP");
     ctx->subwarp = !(v && v[0] == '0');
-    v = std::getenv("DCPGPU_SEGMENTS");
-    ctx->segments = !(v && v[0] == '0');
     if ((v = std::getenv("DCPGPU_COL_BUDGET_MB")) && std::atoll(v) > 0) ctx->col_budget = (size_t)std::atoll(v) << 20;
     if ((v = std::getenv("DCPGPU_LZ_SLACK"))) ctx->lz_slack = std::atoll(v);
   }
@@ -1108,6 +917,7 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_profiles);
   cudaFree(ctx->d_stage);
   cudaFree(ctx->d_words);
+  cudaFree(ctx->d_hist);
   cudaFree(ctx->d_seq_word);
   cudaFree(ctx->d_seq_len);
   for (auto p : ctx->d_xt) cudaFree(p);
@@ -1311,7 +1121,7 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   // Profiles the strip kernels run are also stored as segments: 256 nodes each in the Q = 8
   // full-warp layout, the tail in the layout a profile of its size would get (strip_kernel.cuh).
   int seg_first = -1, seg_count = 0;
-  if (ctx->segments && d.W > 1 && d.W <= 8 && d.Q <= MAXQ_REG) // exactly the strip classes 9..20
+  if (d.W > 1 && d.W <= 8 && d.Q <= MAXQ_REG) // exactly the strip classes 9..20
   {
     seg_first = (int)ctx->h_segs.size();
     for (int k0 = 0; k0 < K; k0 += 256)
@@ -1362,6 +1172,30 @@ int dcpgpu_profile_core_size(dcpgpu_ctx const *ctx, int32_t profile)
   return ctx->h_profiles[(size_t)profile].K;
 }
 
+namespace dcp {
+// Ten-bit history of every position of the packed read stream: hist[g] = nucleotides g-4..g, the
+// most recent in the low two bits (code of the t-mer ending at g = off[t] + (hist[g] & (4^t - 1))).
+// Positions before a window's start only ever meet +INF states, so no per-sequence logic is needed.
+__global__ void hist_kernel(uint32_t const *__restrict__ words, long long nwords, uint16_t *__restrict__ hist,
+                            long long nhist)
+{
+  long long const g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= nhist) return;
+  unsigned h = 0;
+  if (g < nwords * 16)
+  {
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+    {
+      long long const j = g - i;
+      if (j >= 0) h |= ((__ldg(words + (j >> 4)) >> (2 * (int)(j & 15))) & 3u) << (2 * i);
+    }
+  }
+  hist[g] = (uint16_t)h;
+}
+
+} // namespace dcp
+
 int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int64_t const *offsets)
 {
   if (!ctx || nseq < 0 || (nseq > 0 && (!symbols || !offsets))) return fail(ctx, DCPGPU_EINVAL, "reads_set: bad argument");
@@ -1392,6 +1226,8 @@ int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int6
   }
   CU(cudaStreamSynchronize(ctx->stream));
   if (ctx->d_words) CU(cudaFree(ctx->d_words));
+  if (ctx->d_hist) CU(cudaFree(ctx->d_hist));
+  ctx->d_hist = nullptr;
   if (ctx->d_seq_word) CU(cudaFree(ctx->d_seq_word));
   if (ctx->d_seq_len) CU(cudaFree(ctx->d_seq_len));
   ctx->d_words = nullptr;
@@ -1401,6 +1237,13 @@ int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int6
   CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_seq_word), std::max<size_t>(1, seq_word.size()) * sizeof(long long)));
   CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_seq_len), std::max<size_t>(1, seq_len.size()) * sizeof(int)));
   CU(cudaMemcpyAsync(ctx->d_words, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  {
+    long long const nhist = (long long)words.size() * 16 + HIST_SLACK;
+    CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_hist), (size_t)nhist * sizeof(uint16_t)));
+    hist_kernel<<<(unsigned)((nhist + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_words, (long long)words.size(), ctx->d_hist, nhist);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+  }
   if (nseq)
   {
     CU(cudaMemcpyAsync(ctx->d_seq_word, seq_word.data(), seq_word.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
@@ -1468,10 +1311,9 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if ((rc = ensure(ctx, ctx->d_pairs, ctx->pairs_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, (size_t)npairs))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo, ctx->redo_cap, (size_t)npairs))) return rc;
-  // profiles of more than 256 nodes: segment by segment (uniform strips only when segments are switched off)
+  // profiles of more than 256 nodes: segment by segment
   SegPlan seg;
   bool seg_ok = false;
-  if (ctx->segments)
   {
     std::vector<std::pair<int, long long>> entries;
     for (int c = 9; c <= 20; ++c)
@@ -1481,13 +1323,6 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       if ((rc = prepare_segments(ctx, false, entries, 1, maxlen, &seg))) return rc;
       seg_ok = true;
     }
-  }
-  StripPlan plan;
-  if (!seg_ok)
-  {
-    unsigned long long count[NCLASS];
-    for (int c = 0; c < NCLASS; ++c) count[c] = first[c + 1] - first[c];
-    if ((rc = plan_strips(ctx, count, maxlen, &plan))) return rc;
   }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
@@ -1510,7 +1345,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   {
     int const c = launch_order(ci); // longest pairs first: their tail hides under the rest
     size_t const n = first[c + 1] - first[c];
-    if (!n || (seg_ok && c >= 9 && c <= 20)) continue;
+    if (!n || (c >= 9 && c <= 20)) continue; // 9..20 ran as segments above
     ScoreArgs a{};
     a.profiles = ctx->d_profiles;
     a.reads = reads_view(ctx);
@@ -1526,15 +1361,6 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       GenArgs g{};
       g.s = a;
       if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
-    }
-    else if (c >= 9 && c <= 20)
-    { // speculative strips; failures are redone below
-      StripArgs sa{};
-      sa.s = a;
-      sa.redo = ctx->d_redo;
-      sa.nredo = ctx->d_counters + SLOT_NREDO;
-      if ((rc = launch_strip_class(ctx, c, sa, plan))) return rc;
-      any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
       return rc;
@@ -1598,7 +1424,6 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   }
   SegPlan seg;
   bool seg_ok = false;
-  if (ctx->segments)
   {
     std::vector<std::pair<int, long long>> entries;
     for (int c = 9; c <= 20; ++c)
@@ -1608,13 +1433,6 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       if ((rc = prepare_segments(ctx, true, entries, (size_t)nseq, ctx->maxlen, &seg))) return rc;
       seg_ok = true;
     }
-  }
-  StripPlan plan;
-  if (!seg_ok)
-  {
-    unsigned long long count[NCLASS];
-    for (int c = 0; c < NCLASS; ++c) count[c] = (unsigned long long)(first[c + 1] - first[c]) * (unsigned long long)nseq;
-    if ((rc = plan_strips(ctx, count, ctx->maxlen, &plan))) return rc;
   }
   bool any_strip = false;
   CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -1641,7 +1459,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
   {
     int const c = launch_order(ci);
     size_t const n = first[c + 1] - first[c];
-    if (!n || (seg_ok && c >= 9 && c <= 20)) continue;
+    if (!n || (c >= 9 && c <= 20)) continue; // 9..20 ran as segments above
     ScoreArgs a{};
     a.profiles = ctx->d_profiles;
     a.reads = reads_view(ctx);
@@ -1659,15 +1477,6 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       GenArgs g{};
       g.s = a;
       if ((rc = launch_generic<false>(ctx, g, maxK_generic))) return rc;
-    }
-    else if (c >= 9 && c <= 20)
-    { // speculative strips; failures are redone below
-      StripArgs sa{};
-      sa.s = a;
-      sa.redo = ctx->d_redo;
-      sa.nredo = ctx->d_counters + SLOT_NREDO;
-      if ((rc = launch_strip_class(ctx, c, sa, plan))) return rc;
-      any_strip = true;
     }
     else if ((rc = launch_class(ctx, c, a)))
       return rc;

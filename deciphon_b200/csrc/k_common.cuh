@@ -1,0 +1,42 @@
+// Shared by the kernel translation units: persistent-grid launch of a row kernel.
+#pragma once
+#include "kernels.h"
+#include "row_kernel.cuh"
+#include <algorithm>
+
+namespace dcp {
+
+template <int Q, int SEG, int MODE, bool DUMP>
+cudaError_t launch_row_t(StripArgs const &a, int sm_count, cudaStream_t st)
+{
+  constexpr int T = 32 * ROW_WARPS, PER_CTA = ROW_WARPS * (32 / SEG);
+  int per_sm = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_row_kernel<Q, SEG, MODE, DUMP>, T, 0);
+  if (e != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  unsigned long long const want = (a.s.nitems + PER_CTA - 1) / PER_CTA;
+  unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * sm_count);
+  if (grid == 0) return cudaSuccess;
+  score_row_kernel<Q, SEG, MODE, DUMP><<<grid, T, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// Q = 5..8 switch for one (SEG, MODE, DUMP)
+template <int SEG, int MODE, bool DUMP>
+cudaError_t launch_row_q58(int Q, StripArgs const &a, int sm_count, cudaStream_t st)
+{
+  switch (Q)
+  {
+  case 5: return launch_row_t<5, SEG, MODE, DUMP>(a, sm_count, st);
+  case 6: return launch_row_t<6, SEG, MODE, DUMP>(a, sm_count, st);
+  case 7: return launch_row_t<7, SEG, MODE, DUMP>(a, sm_count, st);
+  case 8: return launch_row_t<8, SEG, MODE, DUMP>(a, sm_count, st);
+  default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_row_whole32(int Q, bool dump, StripArgs const &a, int sm_count, cudaStream_t st);
+cudaError_t launch_row_sub(int Q, int SEG, bool dump, StripArgs const &a, int sm_count, cudaStream_t st);
+cudaError_t launch_row_seg(int Q, int SEG, int mode, StripArgs const &a, int sm_count, cudaStream_t st);
+
+} // namespace dcp

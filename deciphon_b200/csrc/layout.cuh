@@ -80,9 +80,11 @@ struct Pair
 struct ReadsView
 {
   uint32_t const *words;
+  uint16_t const *hist;      // [16 * nwords + slack] ten-bit history ending at each position (row_kernel.cuh)
   long long const *seq_word; // [nseq] first word of each sequence
   int const *seq_len;        // [nseq]
   int nseq;
+  int eight;                 // the value 8 as a run-time operand (row_kernel.cuh:mad_ptr)
   long long nwords;          // words in the buffer (sub_kernel.cuh clamps its read-ahead to it)
 };
 
