@@ -40,6 +40,7 @@ SYMBOLS = [
     ("dcpgpu_last_redo", _i64, [_vp]),
     ("dcpgpu_launch_count", _i64, [_vp]),
     ("dcpgpu_alu_peak", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
+    ("dcpgpu_frame_tables", C.c_int, [_vp, _i32, _vp, _vp, _f32, _vp]),
     ("dcpgpu_trace_pairs", C.c_int, [_vp, _i64, _vp, _u32, _vp, _vp]),
     ("dcpgpu_trace_fetch", C.c_int, [_vp, _vp, _vp, _vp]),
     ("dcpgpu_trace_trellis", C.c_int, [_vp, _i64, _vp, _vp]),

@@ -9,6 +9,7 @@
 #include "generic_kernel.cuh"
 #include "layout.cuh"
 #include "kernels.h"
+#include "press_kernel.cuh"
 #include "row_kernel.cuh"
 #include "trace_argmin.cuh"
 #include "trace_walk.cuh"
@@ -1984,6 +1985,30 @@ int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s)
   case 5: return run_alu_peak<5>(ctx, tera_ops_per_s);
   default: return fail(ctx, DCPGPU_EINVAL, "alu_peak: bad mode");
   }
+}
+
+int dcpgpu_frame_tables(dcpgpu_ctx *ctx, int32_t nstates, float const *nuclt_lprobs, float const *codon_marg_lprobs,
+                        float epsilon, float *emission)
+{
+  if (!ctx || nstates < 0 || (nstates && (!nuclt_lprobs || !codon_marg_lprobs || !emission)) || !(epsilon >= 0.f) ||
+      !(epsilon < 1.f))
+    return fail(ctx, DCPGPU_EINVAL, "frame_tables: bad argument");
+  if (nstates == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  size_t const n = (size_t)nstates;
+  size_t const in_floats = n * (4 + 125), out_floats = n * NCODES;
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, in_floats + out_floats))) return rc;
+  float *d_nuclt = ctx->d_scratch, *d_marg = d_nuclt + n * 4, *d_out = d_marg + n * 125;
+  CU(cudaMemcpyAsync(d_nuclt, nuclt_lprobs, n * 4 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_marg, codon_marg_lprobs, n * 125 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  FrameArgs a{d_nuclt, d_marg, d_out, epsilon, nstates};
+  frame_table_kernel<<<(unsigned)nstates, 256, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  CU(cudaMemcpyAsync(emission, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int dcpgpu_xtrans(int window_len, uint32_t flags, float out[13])

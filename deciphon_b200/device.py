@@ -181,6 +181,16 @@ class Device:
         self._check(lib.dcpgpu_alu_peak(self._h, mode, C.byref(v)))
         return v.value
 
+    def frame_tables(self, nuclt_lprobs, codon_marg_lprobs, epsilon: float) -> np.ndarray:
+        """Emission log-prob tables [n][1364] of n frame states (press path, include/dcpgpu.h)."""
+        nu = np.ascontiguousarray(nuclt_lprobs, dtype=np.float32).reshape(-1, 4)
+        cm = np.ascontiguousarray(codon_marg_lprobs, dtype=np.float32).reshape(-1, 125)
+        if len(nu) != len(cm):
+            raise ValueError("one base distribution and one codon marginal table per state")
+        out = np.empty((len(nu), 1364), dtype=np.float32)
+        self._check(lib.dcpgpu_frame_tables(self._h, len(nu), _ptr(nu), _ptr(cm), float(epsilon), _ptr(out)))
+        return out
+
     # -- trace pass ----------------------------------------------------------------------
     def trace_pairs_flat(self, pairs: np.ndarray, multi_hits=True, hmmer3_compat=False, keep_trellis=False):
         """Returns (alt_cost[n], offsets[n+1], state_ids uint16[total], seqsizes uint8[total])."""

@@ -146,6 +146,15 @@ int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t 
  * 1: FADD, 2: FMNMX, 3: FMNMX3 (one op each), 4: FADD2, 5: FADD2+FMNMX3. */
 int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s);
 
+/* ---- press: frame-state emission tables --------------------------------------------------
+ * For each of nstates states, the log-probability of emitting every 1..5-nucleotide fragment
+ * (out[s][1364], the scan's code order) from its base log-probs [4], codon marginal log-probs
+ * [5][5][5] (index 4 = any base) and the indel rate epsilon: what imm_score_table_scores writes
+ * for an imm_frame_state at c-core/protein.c:102, protein_null.c:24, protein_background.c:19.
+ * Host pointers in and out. */
+int dcpgpu_frame_tables(dcpgpu_ctx *ctx, int32_t nstates, float const *nuclt_lprobs,
+                        float const *codon_marg_lprobs, float epsilon, float *emission);
+
 /* The 13 special-transition costs for a window of window_len nucleotides, in the order
  * RR,SN,NN,SB,NB,EB,JB,EJ,JJ,EC,CC,ET,CT (viterbi.h:4-19), as the device uses them. */
 int dcpgpu_xtrans(int window_len, uint32_t flags, float out[13]);
