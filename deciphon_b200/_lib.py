@@ -24,6 +24,7 @@ SYMBOLS = [
     ("dcpgpu_set_stream", C.c_int, [_vp, _vp]),
     ("dcpgpu_sync", C.c_int, [_vp]),
     ("dcpgpu_device_info", _i64, [_vp, C.c_int]),
+    ("dcpgpu_device_count", _i32, []),
     ("dcpgpu_pool_add", C.c_int, [_vp, C.c_int, _vp, _vp, C.POINTER(_i64)]),
     ("dcpgpu_profile_add", C.c_int, [_vp, C.c_int, _vp, _i64, _vp, _vp, _vp, C.POINTER(_i32)]),
     ("dcpgpu_profile_count", C.c_int, [_vp]),
@@ -41,6 +42,9 @@ SYMBOLS = [
     ("dcpgpu_launch_count", _i64, [_vp]),
     ("dcpgpu_alu_peak", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     ("dcpgpu_frame_tables", C.c_int, [_vp, _i32, _vp, _vp, _f32, _vp]),
+    ("dcpgpu_profile_set_decoder", C.c_int, [_vp, _i32, _vp, _vp, _vp, C.c_char_p]),
+    ("dcpgpu_match_build", C.c_int, [_vp, _f32, C.c_int, _vp, _vp, _vp, _vp]),
+    ("dcpgpu_match_fetch", C.c_int, [_vp, _vp]),
     ("dcpgpu_trace_pairs", C.c_int, [_vp, _i64, _vp, _u32, _vp, _vp]),
     ("dcpgpu_trace_fetch", C.c_int, [_vp, _vp, _vp, _vp]),
     ("dcpgpu_trace_trellis", C.c_int, [_vp, _i64, _vp, _vp]),

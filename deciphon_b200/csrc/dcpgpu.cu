@@ -9,6 +9,7 @@
 #include "generic_kernel.cuh"
 #include "layout.cuh"
 #include "kernels.h"
+#include "match_kernel.cuh"
 #include "press_kernel.cuh"
 #include "row_kernel.cuh"
 #include "trace_argmin.cuh"
@@ -68,6 +69,20 @@ struct dcpgpu_ctx
   std::vector<char> h_unsafe; // a cost is negative/NaN: only the generic kernel may run it
   ProfileDesc *d_profiles = nullptr;
   size_t d_profiles_cap = 0;
+  // per-profile decode tables for the match strings (match_kernel.cuh)
+  std::vector<DecoderDesc> h_decoders;
+  DecoderDesc *d_decoders = nullptr;
+  size_t d_decoders_cap = 0;
+  // match pass state
+  int *d_m_hit = nullptr, *d_m_start = nullptr, *d_m_stop = nullptr, *d_m_begin = nullptr, *d_m_end = nullptr, *d_m_bad = nullptr;
+  long long *d_m_len = nullptr, *d_m_off = nullptr;
+  size_t m_cap[7] = {0, 0, 0, 0, 0, 0, 0};
+  uint8_t *d_m_codon = nullptr;
+  char *d_m_amino = nullptr, *d_m_text = nullptr;
+  size_t m_codon_cap = 0, m_amino_cap = 0, m_text_cap = 0, m_bad_cap = 0;
+  std::vector<long long> m_text_off;
+  bool matched = false;
+  bool steps_compact = false;
   // segmented copies of the profiles of more than 256 nodes (strip_kernel.cuh)
   std::vector<ProfileDesc> h_segs;
   std::vector<int> h_seg_first, h_seg_count; // per profile; first = -1: not segmented
@@ -375,6 +390,9 @@ int sync_profiles(dcpgpu_ctx *ctx)
   CU(cudaMemcpyAsync(ctx->d_profiles, ctx->h_profiles.data(), n * sizeof(ProfileDesc),
                      cudaMemcpyHostToDevice, ctx->stream));
   int rc;
+  ctx->h_decoders.resize(n, DecoderDesc{nullptr, {0}});
+  if ((rc = ensure(ctx, ctx->d_decoders, ctx->d_decoders_cap, n))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_decoders, ctx->h_decoders.data(), n * sizeof(DecoderDesc), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = ensure(ctx, ctx->d_seg_first, ctx->d_seg_first_cap, n))) return rc;
   CU(cudaMemcpyAsync(ctx->d_seg_first, ctx->h_seg_first.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if (!ctx->h_segs.empty())
@@ -861,6 +879,7 @@ char const *dcpgpu_strerror(int code)
   case DCPGPU_ENOMEM: return "out of memory";
   case DCPGPU_EINVAL: return "invalid argument";
   case DCPGPU_ESTATE: return "call made in the wrong state";
+  case DCPGPU_EDECODE: return "could not decode a fragment into a codon";
   default: return "unknown dcpgpu error";
   }
 }
@@ -929,6 +948,10 @@ void dcpgpu_close(dcpgpu_ctx *ctx)
   cudaFree(ctx->d_order);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_tpairs);
+  cudaFree(ctx->d_decoders);
+  cudaFree(ctx->d_m_hit); cudaFree(ctx->d_m_start); cudaFree(ctx->d_m_stop); cudaFree(ctx->d_m_begin); cudaFree(ctx->d_m_end);
+  cudaFree(ctx->d_m_bad); cudaFree(ctx->d_m_len); cudaFree(ctx->d_m_off); cudaFree(ctx->d_m_codon); cudaFree(ctx->d_m_amino);
+  cudaFree(ctx->d_m_text);
   cudaFree(ctx->d_xnodes);
   cudaFree(ctx->d_nodes);
   cudaFree(ctx->d_xnode_off);
@@ -995,6 +1018,13 @@ int dcpgpu_sync(dcpgpu_ctx *ctx)
   CU(cudaSetDevice(ctx->device));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
+}
+
+int32_t dcpgpu_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
 }
 
 int64_t dcpgpu_device_info(dcpgpu_ctx const *ctx, int what)
@@ -1561,6 +1591,8 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(cudaSetDevice(ctx->device));
   int rc, maxlen = 1;
   ctx->traced = false;
+  ctx->matched = false;
+  ctx->steps_compact = false;
   if ((rc = check_pairs(ctx, npairs, pairs, &maxlen))) return rc;
   if ((rc = ensure_xt(ctx, flags, maxlen))) return rc;
   if ((rc = sync_profiles(ctx))) return rc;
@@ -1883,16 +1915,14 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   return 0;
 }
 
-int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_ids, uint8_t *seqsizes)
+// Compact device layout of the traced paths: path i at [off[i], off[i] + nsteps[i]) in path order.
+static int compact_steps(dcpgpu_ctx *ctx, std::vector<long long> *off_out)
 {
-  if (!ctx || !ctx->traced) return fail(ctx, DCPGPU_ESTATE, "trace_fetch before trace_pairs");
   size_t const n = ctx->t_pairs.size();
-  if (n == 0) return 0;
-  if (!offsets || !state_ids || !seqsizes) return fail(ctx, DCPGPU_EINVAL, "trace_fetch: bad argument");
-  CU(cudaSetDevice(ctx->device));
-  // device-side compact layout; the caller's offsets may be any non-overlapping placement
   std::vector<long long> off(n + 1, 0);
   for (size_t i = 0; i < n; ++i) off[i + 1] = off[i] + ctx->t_nsteps[i];
+  if (off_out) *off_out = off;
+  if (ctx->steps_compact) return 0;
   size_t const total = (size_t)off[n];
   int rc;
   if ((rc = ensure(ctx, ctx->d_step_off, ctx->step_off_cap, n + 1))) return rc;
@@ -1901,6 +1931,7 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
   uint16_t *d_ids = ctx->d_step_ids;
   uint8_t *d_sz = ctx->d_step_sz;
   CU(cudaMemcpyAsync(ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream)); // off is a local
   if (ctx->t_node_off[n] > 0)
   { // pairs traced through a trellis: second back-walk, in path order
     WalkArgs w{};
@@ -1933,6 +1964,23 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
     CU(cudaGetLastError());
     ctx->launches += 1;
   }
+  ctx->steps_compact = true;
+  return 0;
+}
+
+int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_ids, uint8_t *seqsizes)
+{
+  if (!ctx || !ctx->traced) return fail(ctx, DCPGPU_ESTATE, "trace_fetch before trace_pairs");
+  size_t const n = ctx->t_pairs.size();
+  if (n == 0) return 0;
+  if (!offsets || !state_ids || !seqsizes) return fail(ctx, DCPGPU_EINVAL, "trace_fetch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<long long> off;
+  int rc;
+  if ((rc = compact_steps(ctx, &off))) return rc;
+  size_t const total = (size_t)off[n];
+  uint16_t *d_ids = ctx->d_step_ids;
+  uint8_t *d_sz = ctx->d_step_sz;
   bool compact = true; // the usual placement: paths back to back in pair order
   for (size_t i = 0; i < n && compact; ++i) compact = offsets[i] == offsets[0] + off[i];
   if (compact)
@@ -1985,6 +2033,122 @@ int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s)
   case 5: return run_alu_peak<5>(ctx, tera_ops_per_s);
   default: return fail(ctx, DCPGPU_EINVAL, "alu_peak: bad mode");
   }
+}
+
+int dcpgpu_profile_set_decoder(dcpgpu_ctx *ctx, int32_t profile, float const *node_dists, float const *null_dist,
+                               float const *bg_dist, char const *gencode64)
+{
+  if (!ctx || profile < 0 || (size_t)profile >= ctx->h_profiles.size() || !node_dists || !null_dist || !bg_dist ||
+      !gencode64)
+    return fail(ctx, DCPGPU_EINVAL, "profile_set_decoder: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  int const K = ctx->h_profiles[(size_t)profile].K;
+  void *mem = nullptr;
+  int rc;
+  if ((rc = arena_alloc(ctx, (size_t)(K + 2) * DIST_FLOATS * sizeof(float), &mem))) return rc;
+  float *d = static_cast<float *>(mem);
+  CU(cudaMemcpyAsync(d, node_dists, (size_t)K * DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + (size_t)K * DIST_FLOATS, null_dist, DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + (size_t)(K + 1) * DIST_FLOATS, bg_dist, DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream)); // the caller's buffers may be reused right away
+  ctx->h_decoders.resize(ctx->h_profiles.size(), DecoderDesc{nullptr, {0}});
+  DecoderDesc &dd = ctx->h_decoders[(size_t)profile];
+  dd.dists = d;
+  std::memcpy(dd.gencode, gencode64, 64);
+  ctx->profiles_dirty = true;
+  return 0;
+}
+
+int dcpgpu_match_build(dcpgpu_ctx *ctx, float epsilon, int is_rna, int32_t *hit, int32_t *hit_start, int32_t *hit_stop,
+                       int64_t *text_off)
+{
+  if (!ctx || !ctx->traced) return fail(ctx, DCPGPU_ESTATE, "match_build before trace_pairs");
+  size_t const n = ctx->t_pairs.size();
+  if (text_off) text_off[0] = 0;
+  ctx->m_text_off.assign(n + 1, 0);
+  ctx->matched = true;
+  if (n == 0) return 0;
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = sync_profiles(ctx))) return rc;
+  std::vector<long long> off;
+  if ((rc = compact_steps(ctx, &off))) return rc;
+  size_t const total = (size_t)off[n];
+  if ((rc = ensure(ctx, ctx->d_m_hit, ctx->m_cap[0], n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_start, ctx->m_cap[1], n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_stop, ctx->m_cap[2], n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_begin, ctx->m_cap[3], n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_end, ctx->m_cap[4], n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_len, ctx->m_cap[5], n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_off, ctx->m_cap[6], n + 1))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_bad, ctx->m_bad_cap, 1))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_codon, ctx->m_codon_cap, total))) return rc;
+  if ((rc = ensure(ctx, ctx->d_m_amino, ctx->m_amino_cap, total))) return rc;
+  CU(cudaMemsetAsync(ctx->d_m_bad, 0, sizeof(int), ctx->stream));
+  MatchArgs a{};
+  a.pairs = ctx->d_tpairs;
+  a.npairs = (long long)n;
+  a.nsteps = ctx->d_nsteps;
+  a.step_off = ctx->d_step_off;
+  a.ids = ctx->d_step_ids;
+  a.sizes = ctx->d_step_sz;
+  a.profiles = ctx->d_profiles;
+  a.decoders = ctx->d_decoders;
+  a.reads = reads_view(ctx);
+  a.eps = (double)epsilon;
+  a.is_rna = is_rna;
+  a.hit = ctx->d_m_hit;
+  a.hit_start = ctx->d_m_start;
+  a.hit_stop = ctx->d_m_stop;
+  a.seg_begin = ctx->d_m_begin;
+  a.seg_end = ctx->d_m_end;
+  a.text_len = ctx->d_m_len;
+  a.text_off = ctx->d_m_off;
+  a.codon = ctx->d_m_codon;
+  a.amino = ctx->d_m_amino;
+  a.bad = ctx->d_m_bad;
+  unsigned const grid = (unsigned)((n + MATCH_WARPS - 1) / MATCH_WARPS);
+  match_kernel<false><<<grid, 32 * MATCH_WARPS, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  std::vector<long long> len(n);
+  std::vector<int> h_hit(n), h_start(n), h_stop(n);
+  int bad = 0;
+  CU(cudaMemcpyAsync(len.data(), ctx->d_m_len, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h_hit.data(), ctx->d_m_hit, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h_start.data(), ctx->d_m_start, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(h_stop.data(), ctx->d_m_stop, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(&bad, ctx->d_m_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (bad) return fail(ctx, DCPGPU_EDECODE, "match_build: a fragment could not be decoded into a codon (or no decoder tables)");
+  for (size_t i = 0; i < n; ++i)
+  {
+    ctx->m_text_off[i + 1] = ctx->m_text_off[i] + len[i];
+    if (hit) hit[i] = h_hit[i];
+    if (hit_start) hit_start[i] = h_start[i];
+    if (hit_stop) hit_stop[i] = h_stop[i];
+    if (text_off) text_off[i + 1] = (int64_t)ctx->m_text_off[i + 1];
+  }
+  size_t const bytes = (size_t)ctx->m_text_off[n];
+  if ((rc = ensure(ctx, ctx->d_m_text, ctx->m_text_cap, bytes + 1))) return rc;
+  CU(cudaMemcpyAsync(ctx->d_m_off, ctx->m_text_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  a.text = ctx->d_m_text;
+  match_kernel<true><<<grid, 32 * MATCH_WARPS, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+
+int dcpgpu_match_fetch(dcpgpu_ctx *ctx, char *text)
+{
+  if (!ctx || !ctx->matched) return fail(ctx, DCPGPU_ESTATE, "match_fetch before match_build");
+  size_t const bytes = ctx->m_text_off.empty() ? 0 : (size_t)ctx->m_text_off.back();
+  if (bytes == 0) return 0;
+  if (!text) return fail(ctx, DCPGPU_EINVAL, "match_fetch: bad argument");
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(text, ctx->d_m_text, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int dcpgpu_frame_tables(dcpgpu_ctx *ctx, int32_t nstates, float const *nuclt_lprobs, float const *codon_marg_lprobs,

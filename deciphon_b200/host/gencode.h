@@ -8,6 +8,12 @@
 #include <cmath>
 #include <cstring>
 
+#ifdef __CUDACC__
+#define DCPB_HD __host__ __device__
+#else
+#define DCPB_HD
+#endif
+
 namespace dcpb {
 
 // id -> 64 amino letters in TCAG x TCAG x TCAG codon order (NCBI gc.prt); nullptr: unknown id.
@@ -46,10 +52,12 @@ inline char const *gencode_table(int id)
 }
 
 // amino letter of codon (a, b, c) given as ACGT indices
-inline char codon_amino(char const *table, int a, int b, int c)
+DCPB_HD inline char codon_amino(char const *table, int a, int b, int c)
 {
-  static int const tcag[4] = {2, 1, 3, 0};
-  return table[tcag[a] * 16 + tcag[b] * 4 + tcag[c]];
+  // A, C, G, T -> position in T, C, A, G
+  int const ta = a == 0 ? 2 : a == 1 ? 1 : a == 2 ? 3 : 0, tb = b == 0 ? 2 : b == 1 ? 1 : b == 2 ? 3 : 0,
+            tc = c == 0 ? 2 : c == 1 ? 1 : c == 2 ? 3 : 0;
+  return table[ta * 16 + tb * 4 + tc];
 }
 
 // Base distribution and codon marginals of one state, as stored in a .dcp record (log-probs).
@@ -59,16 +67,12 @@ struct NucltDist
   float codon[125]; // [a][b][c], index 4 = any base (imm_codon_marg)
 };
 
-// log p(codon, fragment z[0..n)) of a frame state with indel rate eps: the emission formula of
-// the frame table (csrc/press_kernel.cuh) with every codon marginal p(pattern) replaced by
-// p(codon) * [codon matches pattern] (third-party imm_frame_cond_lprob).
-inline double frame_joint(NucltDist const &d, double eps, int const codon[3], int const *z, int n)
+// p(codon, fragment z[0..n)) of a frame state with indel rate eps, given pc = p(codon) and the base
+// probabilities b: the emission formula of the frame table (csrc/press_kernel.cuh) with every
+// codon marginal p(pattern) replaced by p(codon) * [codon matches pattern] (third-party
+// imm_frame_cond_lprob).
+DCPB_HD inline double frame_joint_prob(double pc, double const b[4], double eps, int const codon[3], int const *z, int n)
 {
-  double const lp = d.codon[codon[0] * 25 + codon[1] * 5 + codon[2]];
-  if (!(lp > -INFINITY)) return -INFINITY;
-  double const pc = std::exp(lp);
-  double b[4];
-  for (int i = 0; i < 4; ++i) b[i] = std::exp((double)d.nuclt[i]);
   double const e = eps, f = 1.0 - eps;
   auto M = [&](int x, int y, int w) {
     return ((x == 4 || x == codon[0]) && (y == 4 || y == codon[1]) && (w == 4 || w == codon[2])) ? pc : 0.0;
@@ -117,35 +121,37 @@ inline double frame_joint(NucltDist const &d, double eps, int const codon[3], in
       }
     v = e * e * f * f / 10 * two;
   }
-  return v > 0 ? std::log(v) : -INFINITY;
+  return v;
 }
 
-// Most likely codon of a 1..5-nt fragment: argmax over the 64 codons in ACGT-major order, the
-// first maximum wins (imm_frame_cond_decode as called at decoder.c:38-58).  False when no codon
-// can have produced the fragment (the caller reports DCP_EDECODON like decoder.c:52-56).
-inline bool frame_decode(NucltDist const &d, double eps, int const *z, int n, int out[3])
+// Most likely codon of a 1..5-nt fragment: argmax of p(codon, fragment) over the 64 codons in
+// ACGT-major order, the first maximum wins (imm_frame_cond_decode as called at decoder.c:38-58).
+// False when no codon can have produced the fragment (the caller reports DCP_EDECODON like
+// decoder.c:52-56).
+DCPB_HD inline bool frame_decode(NucltDist const &d, double eps, int const *z, int n, int out[3])
 {
-  double best = -INFINITY;
+  double b[4];
+  for (int i = 0; i < 4; ++i) b[i] = exp((double)d.nuclt[i]);
+  double best = 0.0;
   bool found = false;
   for (int a = 0; a < 4; ++a)
-    for (int b = 0; b < 4; ++b)
+    for (int bb = 0; bb < 4; ++bb)
       for (int c = 0; c < 4; ++c)
       {
-        int const codon[3] = {a, b, c};
-        double const v = frame_joint(d, eps, codon, z, n);
-        if (!found || v > best)
+        double const lp = d.codon[a * 25 + bb * 5 + c];
+        if (!(lp > -INFINITY)) continue;
+        int const codon[3] = {a, bb, c};
+        double const v = frame_joint_prob(exp(lp), b, eps, codon, z, n);
+        if (v > best)
         {
-          if (!found || v > best)
-          {
-            best = v;
-            out[0] = a;
-            out[1] = b;
-            out[2] = c;
-          }
+          best = v;
+          out[0] = a;
+          out[1] = bb;
+          out[2] = c;
           found = true;
         }
       }
-  return found && best > -INFINITY;
+  return found;
 }
 
 } // namespace dcpb

@@ -1,10 +1,13 @@
-"""Mirror of python-core's Scan / Batch / Sequence (python-core/deciphon_core/scan.py:23-83,
-batch.py:8-33, sequence.py) over libdeciphon_b200.so -- same constructor arguments, same
-methods, same error type behaviour (a DeciphonError carrying the C error code)."""
+"""Mirror of python-core's Scan / Batch / Sequence / PressContext (python-core/deciphon_core/
+scan.py:23-83, batch.py:8-33, sequence.py, press.py:9-56) over libdeciphon_b200.so -- same
+constructor arguments, same methods, same error type behaviour (a DeciphonError carrying the C
+error code) -- plus the snap archive step of deciphon_schema.NewSnapFile.make_archive
+(schema/deciphon_schema/__init__.py:221-226): products.tsv + hmmer/ zipped into a .dcs file."""
 from __future__ import annotations
 
 import ctypes as C
 import os
+import shutil
 from dataclasses import dataclass
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -35,6 +38,7 @@ SYMBOLS = [
     ("dcp_batch_reset", None, [C.c_void_p]),
     ("dcp_error_string", C.c_char_p, [C.c_int]),
     ("dcpb200_db_info", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_float)]),
+    ("dcpb200_scan_num_gpus", C.c_int, [C.c_void_p]),
 ]
 
 
@@ -91,7 +95,10 @@ class Batch:
 
 
 class Scan:
-    def __init__(self, dbfile, port: int, num_threads: int, multi_hits: bool, hmmer3_compat: bool, cache: bool):
+    def __init__(self, dbfile, port: int, num_threads: int, multi_hits: bool, hmmer3_compat: bool, cache: bool,
+                 on_callback=None):
+        """on_callback(scan): optional hook run inside the C callback (python-core's is a no-op that
+        only lets Python signal handlers run, scan.py:13-21); tests use it to interrupt a run."""
         self._cscan = lib.dcp_scan_new()
         if not self._cscan:
             raise MemoryError()
@@ -100,6 +107,8 @@ class Scan:
 
         def _cb(_userdata):
             self.callbacks += 1
+            if on_callback is not None:
+                on_callback(self)
 
         self._cb = _CALLBACK(_cb)  # keep alive
         path = str(getattr(dbfile, "path", dbfile)).encode()
@@ -123,6 +132,11 @@ class Scan:
     def progress(self) -> int:
         return lib.dcp_scan_progress(self._cscan)
 
+    @property
+    def num_gpus(self) -> int:
+        """GPUs (= profile shards) this scan runs on."""
+        return lib.dcpb200_scan_num_gpus(self._cscan)
+
     def free(self):
         if getattr(self, "_cscan", None):
             lib.dcp_scan_del(self._cscan)
@@ -136,6 +150,77 @@ class Scan:
 
     def __exit__(self, *_):
         self.free()
+
+
+class PressContext:
+    """python-core/deciphon_core/press.py:9-56: hmm -> .dcp, one profile per next()."""
+
+    def __init__(self, hmm, gencode: int, epsilon: float = 0.01, dbpath=None):
+        self._cpress = lib.dcp_press_new()
+        if not self._cpress:
+            raise MemoryError()
+        self._hmm = str(getattr(hmm, "path", hmm))
+        if dbpath is None:
+            dbpath = getattr(getattr(hmm, "dbpath", None), "path", None) or os.path.splitext(self._hmm)[0] + ".dcp"
+        self._db = str(dbpath)
+        if rc := lib.dcp_press_setup(self._cpress, int(gencode), float(epsilon)):
+            raise DeciphonError(rc)
+
+    def open(self):
+        if rc := lib.dcp_press_open(self._cpress, self._hmm.encode(), self._db.encode()):
+            raise DeciphonError(rc)
+
+    def close(self):
+        if rc := lib.dcp_press_close(self._cpress):
+            raise DeciphonError(rc)
+
+    def end(self) -> bool:
+        return bool(lib.dcp_press_end(self._cpress))
+
+    def next(self):
+        if rc := lib.dcp_press_next(self._cpress):
+            raise DeciphonError(rc)
+
+    def __enter__(self):
+        self.open()
+        return self
+
+    def __exit__(self, *_):
+        self.close()
+
+    @property
+    def nproteins(self) -> int:
+        return lib.dcp_press_nproteins(self._cpress)
+
+    def __del__(self):
+        if getattr(self, "_cpress", None):
+            lib.dcp_press_del(self._cpress)
+            self._cpress = None
+
+
+def press(hmm: str, dbpath: str, gencode: int = 1, epsilon: float = 0.01) -> int:
+    """Press every profile of a HMMER3 file (what `deciphon press` drives, cli press loop)."""
+    with PressContext(hmm, gencode, epsilon, dbpath) as ctx:
+        n = 0
+        while True:
+            ctx.next()
+            if ctx.end():
+                break
+            n += 1
+    return n
+
+
+def make_snap_archive(basedir: str, dcs_path: str) -> str:
+    """NewSnapFile.make_archive: zip `<basedir>` (products.tsv + hmmer/) into `<name>.dcs`, the
+    layout deciphon_snap.SnapFile reads (snap/deciphon_snap/snap_file.py:18-33: one root directory
+    holding products.tsv and hmmer/).  Without the HMMER stage (port <= 0) hmmer/ is empty."""
+    basedir = os.path.abspath(str(basedir))
+    if not str(dcs_path).endswith(".dcs"):
+        raise ValueError("must end in `.dcs`")
+    x = shutil.make_archive(basedir, "zip", os.path.dirname(basedir), os.path.basename(basedir))
+    shutil.move(x, str(dcs_path))
+    shutil.rmtree(basedir)
+    return str(dcs_path)
 
 
 def db_info(path: str):

@@ -48,6 +48,7 @@ enum
   DCPGPU_ENOMEM = 3,    /* host or device allocation failed */
   DCPGPU_EINVAL = 4,    /* bad argument (range, NULL, ordering) */
   DCPGPU_ESTATE = 5,    /* call made in the wrong state (e.g. fetch before trace) */
+  DCPGPU_EDECODE = 6,   /* a path fragment no codon can have produced (decoder.c:52-56), or no decode tables */
 };
 
 /* flags for score/trace: the two booleans of dcp_scan_setup (deciphon.h:11-13) */
@@ -78,6 +79,8 @@ int dcpgpu_set_stream(dcpgpu_ctx *ctx, void *cuda_stream);
 int dcpgpu_sync(dcpgpu_ctx *ctx);
 /* device facts: 0 = SM count, 1 = total bytes, 2 = free bytes, 3 = bytes held by profiles */
 int64_t dcpgpu_device_info(dcpgpu_ctx const *ctx, int what);
+/* CUDA devices visible to this process (0 when there is no driver or no device). */
+int32_t dcpgpu_device_count(void);
 
 /* ---- profiles ("work_setup": a profile becomes resident) -------------------------------
  * Nodes are uploaded in .dcp form (natural-log probabilities, protein.c:234-281):
@@ -145,6 +148,21 @@ int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t 
  * roofline denominator of the score kernel).  mode 0: FADD+FMNMX 1:1 (the DP's mix),
  * 1: FADD, 2: FMNMX, 3: FMNMX3 (one op each), 4: FADD2, 5: FADD2+FMNMX3. */
 int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s);
+
+/* ---- match strings: the post-processing of a traced path, on the device --------------------
+ * Decode tables of a profile: node_dists[K][129], null_dist[129], bg_dist[129] (4 base log-probs
+ * then 125 codon marginal log-probs [a][b][c], index 4 = any base -- the nuclt_dist of a .dcp
+ * record, nuclt_dist.c:13-20) and the genetic code as 64 amino letters in TCAG x TCAG x TCAG order. */
+int dcpgpu_profile_set_decoder(dcpgpu_ctx *ctx, int32_t profile, float const *node_dists,
+                               float const *null_dist, float const *bg_dist, char const *gencode64);
+/* For every pair of the preceding dcpgpu_trace_pairs: whether the path has a B..E segment, its
+ * window-relative extent (thread.c:130-166) and the bytes of the row's match column
+ * ("<fragment>,<state>,<codon>,<amino>" joined by ';': match.c:66-90, product_thread.c:112-148,
+ * codons by the frame-state decoder of decoder.c:38-58).  text_off[npairs + 1] receives where
+ * each pair's bytes start in the buffer dcpgpu_match_fetch fills.  Any output may be NULL. */
+int dcpgpu_match_build(dcpgpu_ctx *ctx, float epsilon, int is_rna, int32_t *hit, int32_t *hit_start,
+                       int32_t *hit_stop, int64_t *text_off);
+int dcpgpu_match_fetch(dcpgpu_ctx *ctx, char *text);
 
 /* ---- press: frame-state emission tables --------------------------------------------------
  * For each of nstates states, the log-probability of emitting every 1..5-nucleotide fragment

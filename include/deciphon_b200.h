@@ -7,15 +7,21 @@
  * loop of c-core/thread.c:49-208 runs as waves of batched GPU passes through the C ABI of
  * include/dcpgpu.h.  What differs from the reference, by design:
  *
- *   * dcp_scan_setup: `num_threads` and `cache` are accepted and ignored (the GPU holds every
- *     profile resident; c-core/scan.c:95-152).  The environment variable DCP_GPU_DEVICE picks
- *     the CUDA device (default 0).
+ *   * dcp_scan_setup: the reference cuts the database into `num_threads` partitions, one per
+ *     OpenMP thread (c-core/scan.c:95-152); here a partition is a GPU: min(num_threads, visible
+ *     CUDA devices, $DCP_GPU_COUNT) shards of contiguous profiles balanced by core size, starting
+ *     at device $DCP_GPU_DEVICE (default 0), one host thread each.  `cache` is accepted and
+ *     ignored (every profile is resident in HBM).  Rows come out in the reference's order
+ *     whatever the number of shards.  The callback fires on shard 0 after every chunk of profiles
+ *     (the reference: on partition 0 after every window); dcp_scan_interrupt is honoured between
+ *     chunks ($DCP_CHUNK_CELLS DP cells each, default 4e10, about 0.1 s of GPU time).
  *   * HMMER daemon (c-core/hmmer.c, thread.c:185-203): the third-party client libraries are
  *     not part of this build.  `port <= 0` runs WITHOUT the HMMER confirmation stage: every
  *     window with lrt >= 0 and a B..E segment yields a row, `evalue` is written as 0 and no
  *     .h3r files are produced.  `port > 0` returns DCP_EH3CDIAL.
- *   * dcp_press_* (c-core/press.c) is outside the hot path: the functions exist and return
- *     DCP_EFUNCUSE.
+ *   * dcp_press_* (c-core/press.c): HMMER3 ASCII -> .dcp in the reference's current encoding
+ *     (minifam.hmm -> 3,609,858 bytes, test_press.c:26); the frame-state emission tables are
+ *     computed on the GPU.  entry_dist is occupancy-based (press.c:60).
  *   * new error codes are appended after DCP_EINVALNUMPROTEINS = 80.
  */
 #ifndef DECIPHON_B200_H
@@ -58,6 +64,8 @@ char const *dcp_error_string(int error_code);
 /* Extension: parse a .dcp database (either float encoding) without touching
  * the GPU; reports the number of profiles, the total core size and epsilon. */
 int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size, float *epsilon);
+/* Extension: GPUs (= profile shards) a set-up scan runs on. */
+int dcpb200_scan_num_gpus(struct dcp_scan const *);
 
 /* Error codes 1..80 are the reference's (c-core/deciphon.h:34-116); only the ones this
  * library can return are named here.  81.. are new. */
@@ -69,17 +77,22 @@ enum
   DCP_EFWRITE = 9,
   DCP_EZEROSEQ = 11,
   DCP_EDECODON = 14,
+  DCP_ELARGEMODEL = 15,
+  DCP_EREADHMMER3 = 17,
   DCP_ENOMEM = 20,
   DCP_EOPENDB = 21,
+  DCP_EOPENHMM = 22,
   DCP_EWRITEPROD = 39,
   DCP_ELONGACCESSION = 41,
   DCP_EMANYTHREADS = 42,
   DCP_EMKDIR = 45,
+  DCP_ESETGENCODE = 49,
   DCP_EGENCODEID = 50,
   DCP_EH3CDIAL = 51,
   DCP_ESEQABC = 57,
   DCP_ELARGECORESIZE = 63,
   DCP_EENDOFFILE = 66,
+  DCP_EENDOFNODES = 67,
   DCP_EDBVERSION = 68,
   DCP_ENOTDBFILE = 69,
   DCP_ENUCLTNOSUPPORT = 71,

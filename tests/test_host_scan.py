@@ -34,13 +34,21 @@ def test_host_library_exports_reference_api():
     assert sorted(n for n, _, _ in scan.SYMBOLS) == names
 
 
-def test_error_strings_and_press_stub():
+def test_error_strings_and_press_errors(tmp_path):
+    import torch
     from deciphon_b200 import scan
     assert scan.lib.dcp_error_string(20) == b"out of memory"
     assert b"no CUDA device" in scan.lib.dcp_error_string(81)
     assert scan.lib.dcp_error_string(999).startswith(b"unknown error #999")
     p = scan.lib.dcp_press_new()
-    assert scan.lib.dcp_press_open(p, b"x.hmm", b"x.dcp") == 8  # DCP_EFUNCUSE: press is out of the hot path
+    assert scan.lib.dcp_press_open(p, b"x.hmm", b"x.dcp") == 49  # DCP_ESETGENCODE: setup comes first
+    assert scan.lib.dcp_press_setup(p, 7, 0.01) == 50            # DCP_EGENCODEID (press.c:55-56): no NCBI table 7
+    assert scan.lib.dcp_press_setup(p, 1, 0.01) == 0
+    assert scan.lib.dcp_press_open(p, str(tmp_path / "missing.hmm").encode(), str(tmp_path / "x.dcp").encode()) == 22
+    if not torch.cuda.is_available():  # no CPU fallback: the frame tables are computed on the GPU
+        hmm = os.path.join(GOLDEN, "minifam.hmm")
+        assert scan.lib.dcp_press_open(p, hmm.encode(), str(tmp_path / "x.dcp").encode()) == 81
+        assert not (tmp_path / "x.dcp.records.tmp").exists()
     scan.lib.dcp_press_del(p)
 
 
