@@ -13,11 +13,23 @@ total core size), every rank sees every read, no collective on the data path.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
-Prints ONE JSON line (rank 0).  `value` = GCUPS with the reads already resident in HBM;
-`e2e` = the same through the public API with HOST buffers (pack + H2D + D2H inside the timed
-region); `roofline` = the score kernel against the measured FP32 non-tensor issue rate;
-`cpu_baseline` / `--impl reference` = the reference's own viterbi.c/trellis.c (oracle/_ref,
-compiled from /root/reference) driven like its scan loop on all host cores.
+Prints ONE JSON line (rank 0).
+  `value`    GCUPS of full steps through the C ABI (include/dcpgpu.h) with the reads resident in
+             HBM: every window.c window of every pair (profiles of fewer than 40 nodes take two or
+             three windows per 2,000-nt read), CUDA events, max over ranks.
+  `e2e`      the same batches through the REFERENCE API, dcp_scan_setup / dcp_scan_run of
+             libdeciphon_b200.so (include/deciphon_b200.h): the database is a real .dcp file
+             written to local disk, reads are host strings in a dcp_batch, and every step ends
+             with its products.tsv on disk (encode, H2D, D2H, row formatting and file writing
+             inside the timed region).  At N > 1 one process drives the N GPUs as N profile
+             shards (num_threads = N), exactly what a caller of the reference API gets.
+  `e2e_cabi` the same batches through the C ABI with host buffers (no row formatting).
+  `roofline` the score kernels against the FP32 issue ceiling (and the best measured add/min mix).
+  `strong`   (N > 1) a fixed 96-read batch over the N shards, beside the weak-scaling `value`.
+  `configs`  (N = 1) timed legs of BASELINE.json configs 2 and 5 through dcp_scan_run, each
+             checked in the run against the reference's own CPU code (cpu_baseline leg).
+  `cpu_baseline` / `--impl reference`: the reference's viterbi.c/trellis.c/xtrans.c (oracle/_ref,
+             compiled from /root/reference) driven like its scan loop on all host cores.
 """
 from __future__ import annotations
 
@@ -64,6 +76,10 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline leg (and cap of a reference-arm step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-plugin", action="store_true", help="skip the dcp_scan_run legs (e2e falls back to the C ABI leg)")
+    ap.add_argument("--plugin-profiles", type=int, default=0,
+                    help="profiles of the database the dcp_scan_run leg scans (0 = all; fewer if the disk has no room)")
+    ap.add_argument("--tmp", default=os.environ.get("DCP_BENCH_TMP", ""), help="directory for the .dcp file and products")
     return ap.parse_args()
 
 
@@ -191,14 +207,41 @@ def cpu_scan_sample(args, sizes, pool, target_seconds, simd=None):
             "reads": reads}
 
 
-def cpu_baseline_record(args, sizes, pool):
+def cpu_small_configs(args, pool, gpu_small):
+    """Configs 2 and 5 on the reference's own CPU code (oracle/_ref), one thread per profile up to
+    the core count like scan.c:105, and the in-run parity check of the GPU legs: the DP cells of a
+    run (every window start depends on the hits decoded before it) and the number of windows that
+    passed the lrt gate must be identical."""
+    from oracle.oracle import Reference, ref_lib_path
+    ref = Reference(ref_lib_path())
+    out = {}
+    for name, (profs, reads, _text) in small_config_workloads(args, pool).items():
+        rp = [ref.profile(p.costs()) for p in profs]
+        threads = min(len(rp), os.cpu_count() or 1)
+        ref.scan(rp, reads[:1], True, False, threads)
+        r = ref.scan(rp, reads, True, False, threads)
+        rec = {"gcups": r["cells"] / r["seconds"] / 1e9, "reads_per_s": len(reads) / r["seconds"], "ms_per_run": 1e3 * r["seconds"],
+               "threads": threads, "cells": r["cells"], "lrt_windows": int(r["hits"]), "kind": "reference"}
+        g = (gpu_small or {}).get(name)
+        if isinstance(g, dict) and "cells" in g:
+            rec["parity_with_gpu_leg"] = bool(g["cells"] == r["cells"] and g["lrt_windows"] == int(r["hits"]))
+        out[name] = rec
+    return out
+
+
+def cpu_baseline_record(args, sizes, pool, gpu_small=None):
     """cpu_baseline of the measured arm: the widest SIMD build this host runs, plus the reference
-    Makefile's default level (-mavx2, c-core/Makefile:10-12) on a third of the sample."""
+    Makefile's default level (-mavx2, c-core/Makefile:10-12) on a third of the sample, plus the
+    CPU side (and parity check) of the config 2 / config 5 legs."""
     c = cpu_scan_sample(args, sizes, pool, args.cpu_seconds)
     rec = {"value": c["gcups"], "unit": "GCUPS", "cores": c["cores"], "kind": "reference", "sample": c["sample"],
            "parallel_efficiency": c["parallel_efficiency"]}
     wide = os.path.basename(c["ref"].path)
     c.clear()
+    try:
+        rec["configs"] = cpu_small_configs(args, pool, gpu_small)
+    except Exception as e:
+        rec["configs"] = {"unavailable": f"{type(e).__name__}: {e}"}
     if "avx512" in wide:
         try:
             d = cpu_scan_sample(args, sizes, pool, max(3.0, args.cpu_seconds / 3), simd="avx2")
@@ -260,42 +303,192 @@ def workload_config(args, sizes, shard):
 
 # ---- B200 leg -------------------------------------------------------------------------------
 
+def to_text(x: np.ndarray) -> str:
+    return np.frombuffer(b"ACGT", dtype=np.uint8)[x].tobytes().decode()
+
+
+def tmp_root(args, need_bytes: int):
+    """A fresh directory on a local file system with room for need_bytes, else None."""
+    import shutil
+    import tempfile
+    cands = [args.tmp] if args.tmp else ["/tmp", "/var/tmp", "/dev/shm"]
+    for c in cands:
+        try:
+            os.makedirs(c, exist_ok=True)
+            free = shutil.disk_usage(c).free
+            if c.startswith("/dev/shm"):  # RAM: leave room for the page cache of the read-back and the host copies
+                import psutil
+                free = min(free, psutil.virtual_memory().available // 3)
+            if free > need_bytes * 1.1 + (2 << 30):
+                return tempfile.mkdtemp(prefix="dcpbench_", dir=c)
+        except Exception:
+            continue
+    return None
+
+
+def plugin_leg(args, world, sizes, pool, nodes_of, reads, R, nsteps_total):
+    """`e2e`: the batches of the measured leg through dcp_scan_setup / dcp_scan_run (reference API,
+    libdeciphon_b200.so) on a .dcp file of the same synthetic database.  One process, `world` GPUs."""
+    import shutil
+
+    from deciphon_b200.scan import Batch, Scan, Sequence
+    nprof = min(args.plugin_profiles or len(sizes), len(sizes))
+    root = None
+    while True:
+        need = (int(sizes[:nprof].sum()) + nprof) * 6037 + nprof * 32768
+        root = tmp_root(args, need)
+        if root is not None or nprof <= 250:
+            break
+        nprof //= 2  # no room for the whole database: scan a prefix of it and say so
+    if root is None:
+        return {"unavailable": "no local directory with room for the .dcp file"}
+    db = os.path.join(root, "bench.dcp")
+    out = os.path.join(root, "products")
+    try:
+        t0 = time.perf_counter()
+        info = synth.write_synth_dcp(db, sizes, pool, nodes_of, count=nprof)
+        write_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        scan = Scan(db, 0, world, True, False, False)
+        setup_s = time.perf_counter() - t0
+        texts = [to_text(r) for r in reads]
+
+        def step(i):
+            batch = Batch()
+            for j in range(i * R, (i + 1) * R):
+                batch.add(Sequence(j, "read%d" % j, texts[j]))
+            scan.run(out, batch)
+
+        for i in range(args.warmup):
+            step(i)
+        c0 = scan.counters()
+        t0 = time.perf_counter()
+        for i in range(args.warmup, nsteps_total):
+            step(i)
+        secs = time.perf_counter() - t0
+        c1 = scan.counters()
+        d = {k: c1[k] - c0[k] for k in c0}
+        with open(os.path.join(out, "products.tsv"), "rb") as fh:
+            tsv = fh.read()
+        gpus = scan.num_gpus
+        scan.free()
+        return {"value": d["cells"] / secs / 1e9, "unit": "GCUPS", "seconds": secs, "cells": d["cells"],
+                "h2d_bytes_per_step": int(d["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(d["d2h_bytes"] / args.steps),
+                "launches": int(d["launches"]), "windows": int(d["windows"]), "lrt_windows": int(d["lrt_windows"]),
+                "reads_per_s": args.steps * R / secs, "gpus": gpus, "profiles": nprof,
+                "dcp_bytes": info["bytes"], "dcp_write_s": write_s, "setup_s": setup_s,
+                "rows_last_step": tsv.count(b"\n") - 1, "tsv_bytes_last_step": len(tsv),
+                "api": "dcp_batch_add x reads + dcp_scan_run -> products.tsv (libdeciphon_b200.so), num_threads = %d" % world,
+                "dir": os.path.dirname(root)}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def small_config_workloads(args, pool):
+    """BASELINE.json configs 2 and 5 (SURVEY 8d recipes), seed-fixed."""
+    rng = np.random.default_rng([args.seed, 25])
+    p3 = synth.synth_profile(rng, 3, pool, name="MASSIVE3")  # the shape of c-core/massive.hmm (LENG 3)
+    r2 = [synth.fixed_length(rng, synth.mutate(rng, synth.random_read(rng, 1000), 0.10), 1000) for _ in range(1000)]
+    profs5 = [synth.synth_profile(rng, K, pool, name="C5_%d" % K) for K in (50, 100, 200, 500, 1000, 2000)]
+    parts = []
+    for g in range(25):  # ~25 embedded genes
+        p = profs5[g % len(profs5)]
+        cons = np.argmax(p.emission[:p.core_size, 20:84], axis=1)
+        cons = np.stack([cons // 16, (cons // 4) % 4, cons % 4], axis=1).reshape(-1).astype(np.uint8)
+        a = 3 * int(rng.integers(0, max(1, (len(cons) - 600) // 3 + 1)))
+        parts += [synth.random_read(rng, int(rng.integers(200, 500))), cons[a:a + 600]]
+    x5 = synth.fixed_length(rng, synth.mutate(rng, np.concatenate(parts), 0.10), 24000)
+    return {"config2": ([p3], r2, "K = 3 profile (massive.hmm shape, synthetic nodes) vs 1,000 reads x 1,000 nt, 10% errors; "
+                                  "150-nt window.c windows"),
+            "config5": (profs5, [x5], "one 24,000-nt read (25 embedded genes, 10% errors) vs profiles of 50/100/200/500/1000/2000 "
+                                      "nodes; window.c windows, full traceback of every lrt >= 0 window")}
+
+
+def small_config_legs(args, pool):
+    """Timed dcp_scan_run legs of configs 2 and 5 on one GPU (rows written, every window)."""
+    import shutil
+
+    from deciphon_b200.dcp_file import write_dcp
+    from deciphon_b200.scan import Batch, Scan, Sequence
+    root = tmp_root(args, 64 << 20)
+    res = {}
+    if root is None:
+        return res
+    try:
+        for name, (profs, reads, text) in small_config_workloads(args, pool).items():
+            db = os.path.join(root, name + ".dcp")
+            write_dcp(db, profs)
+            texts = [to_text(r) for r in reads]
+            with Scan(db, 0, 1, True, False, False) as scan:
+                def run():
+                    batch = Batch()
+                    for j, t in enumerate(texts):
+                        batch.add(Sequence(j, "r%d" % j, t))
+                    scan.run(os.path.join(root, name), batch)
+                run()  # warm-up
+                reps = 3
+                c0 = scan.counters()
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    run()
+                secs = (time.perf_counter() - t0) / reps
+                c1 = scan.counters()
+            rows = open(os.path.join(root, name, "products.tsv"), "rb").read().count(b"\n") - 1
+            cells = (c1["cells"] - c0["cells"]) / reps
+            res[name] = {"workload": text, "gcups": cells / secs / 1e9, "reads_per_s": len(reads) / secs, "ms_per_run": 1e3 * secs,
+                         "cells": cells, "windows": int((c1["windows"] - c0["windows"]) / reps),
+                         "lrt_windows": int((c1["lrt_windows"] - c0["lrt_windows"]) / reps), "rows": rows,
+                         "launches_per_run": int((c1["launches"] - c0["launches"]) / reps),
+                         "api": "dcp_scan_run (libdeciphon_b200.so), host strings in, products.tsv out, 1 GPU"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return res
+
+
 def run_b200(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
 
+    from deciphon_b200 import waves
     from deciphon_b200.device import PAIR_DTYPE, Device
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (deciphon_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line unless the caller asks for more
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")  # host-side waits (no kernel spinning on a GPU another leg uses)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_ranks(x: float, op) -> float:
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.MAX) if world > 1 else x
+
+    def sum_over_ranks(x):
+        return reduce_ranks(x, dist.ReduceOp.SUM) if world > 1 else x
 
     pool = synth.NodePool()
     sizes = synth.core_sizes(np.random.default_rng(args.seed), args.profiles)
     cuts = shard_bounds(sizes, world)
     p0, p1 = cuts[rank], cuts[rank + 1]
+    nodes = {}
+
+    def nodes_of(p):
+        if p not in nodes:
+            nodes[p] = profile_nodes(args.seed, p, sizes[p], pool)
+        return nodes[p]
 
     dev = Device(local_rank)
     stream = torch.cuda.current_stream()
@@ -303,131 +496,182 @@ def run_b200(args, rank, local_rank, world):
     t_build = time.time()
     first = dev.pool_add(pool.emission, pool.trans)
     for p in range(p0, p1):
-        ids, bmk = profile_nodes(args.seed, p, sizes[p], pool)
+        ids, bmk = nodes_of(p)
         dev.profile_add(int(sizes[p]), bmk, pool.null_emission, pool.bg_emission, ids + first)
     dev.sync()
     t_build = time.time() - t_build
     nprof = p1 - p0
-    R, L = args.reads_per_step * world, args.read_len  # the batch grows with the GPUs: per-rank work fixed
+    Ks = sizes[p0:p1]
+    L = args.read_len
     nsteps_total = args.warmup + args.steps
+    multi_window = int(np.count_nonzero(np.minimum(Ks * 50, 100000) < L))
+
+    def run_legs(R, reads, host_buffers):
+        """args.warmup + args.steps steps of R reads each.  host_buffers: the step's reads are
+        handed over as host symbols (packed + copied inside the step) and every score comes back."""
+        win = np.minimum(np.minimum(Ks * 50, 100000), L).astype(np.int32)  # first window per profile
+        lens = np.full(R, L, dtype=np.int64)
+        offs = np.arange(R + 1, dtype=np.int64) * L
+        pinned = None
+        if host_buffers:
+            pinned = [torch.from_numpy(np.concatenate(reads[i * R:(i + 1) * R])).pin_memory() for i in range(nsteps_total)]
+        else:
+            dev.set_reads(reads)
+
+        def step(i, st):
+            seq0 = 0 if host_buffers else i * R
+            if host_buffers:
+                dev.set_reads_packed(pinned[i].numpy(), offs)
+            dev.score_grid(0, nprof, seq0, seq0 + R, True, False)
+            if host_buffers:
+                dev.scores_fetch(nprof * R)
+            idx = dev.hits_fetch()
+            pr = np.zeros(len(idx), dtype=PAIR_DTYPE)
+            pr["profile"], pr["seq"], pr["start"], pr["len"] = idx // R, seq0 + idx % R, 0, win[idx // R]
+            st["score_ms"] += dev.last_kernel_ms()
+            st["grid_cells"] += dev.last_cells()
+            hit, _hs, he, nst = waves.trace_hits(dev, pr, True, False, Ks=Ks)
+            st["steps"] += nst
+            st["hits"] += len(pr)
+            if multi_window:  # windows 2.. of the profiles of fewer than L/50 nodes (window.c:13-37)
+                w = waves.later_waves(dev, Ks, seq0, lens, pr, hit, he, True, False)
+                st["hits"] += w["hits"]
+                st["steps"] += w["steps"]
+                st["later_windows"] += w["pairs"]
+
+        zero = lambda: {"score_ms": 0.0, "grid_cells": 0.0, "hits": 0, "steps": 0, "later_windows": 0}  # noqa: E731
+        st = zero()
+        for i in range(args.warmup):
+            step(i, st)
+        st = zero()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        c0 = dev.counters()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for i in range(args.warmup, nsteps_total):
+            step(i, st)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        c1 = dev.counters()
+        st["ms"] = max_over_ranks(e0.elapsed_time(e1))
+        st["wall_s"] = max_over_ranks(wall)
+        st["clocks"] = sampler.summary()
+        for k in c0:
+            st[k] = c1[k] - c0[k]
+        st["total_cells"] = sum_over_ranks(st["cells"])
+        st["total_hits"] = sum_over_ranks(float(st["hits"]))
+        return st
+
+    # ---- phase 1: reads resident in HBM ("value", weak scaling: 96 reads per GPU per step) ----
+    R = args.reads_per_step * world
     reads = make_reads(args.seed, 0, nsteps_total * R, L, sizes, pool)
-    win = np.minimum(np.minimum(sizes[p0:p1] * 50, 100000), L).astype(np.int32)  # first window per profile
+    v = run_legs(R, reads, host_buffers=False)
+    # ---- phase 2: the same steps through the C ABI with host buffers ("e2e_cabi") ----
+    c = run_legs(R, reads, host_buffers=True)
+    # ---- phase 3 (N > 1): strong scaling, a fixed batch of 96 reads over the N shards ----
+    strong = None
+    if world > 1:
+        sr = run_legs(args.reads_per_step, reads[: nsteps_total * args.reads_per_step], host_buffers=False)
+        strong = {"value": sr["total_cells"] / (sr["ms"] * 1e-3) / 1e9, "unit": "GCUPS", "reads_per_step": args.reads_per_step,
+                  "ms_per_step": sr["ms"] / args.steps, "scaling": "strong"}
+    # roofline inputs before the context goes away
+    peaks = {}
+    if rank == 0:
+        for name, mode in (("fadd_vimnmx3_2to1", 6), ("fadd_fmnmx3_2to1", 5), ("fadd_fmnmx_1to1", 0), ("fadd", 1)):
+            try:
+                peaks[name] = dev.alu_peak(mode)
+            except Exception:
+                peaks[name] = None
+    db_bytes = dev.profile_bytes
+    dev.close()
+    torch.cuda.empty_cache()
+    score_ms_max = max_over_ranks(v["score_ms"])
 
-    def hit_pairs(seq0):
-        idx = dev.hits_fetch()
-        pr = np.zeros(len(idx), dtype=PAIR_DTYPE)
-        pr["profile"] = idx // R
-        pr["seq"] = seq0 + idx % R
-        pr["start"] = 0
-        pr["len"] = win[idx // R]
-        return pr
-
-    def step_resident(i, stats):
-        seq0 = i * R
-        dev.score_grid(0, nprof, seq0, seq0 + R, True, False)
-        pr = hit_pairs(seq0)
-        stats["score_ms"] += dev.last_kernel_ms()
-        stats["cells"] += dev.last_cells()
-        if len(pr):
-            _, off, _ids, _sz = dev.trace_pairs_flat(pr, True, False)
-            stats["steps"] += int(off[-1])
-        stats["hits"] += len(pr)
-
-    # ---- phase 1: reads resident in HBM ("value") ----
-    dev.set_reads(reads)
-    stats = {"score_ms": 0.0, "cells": 0.0, "hits": 0, "steps": 0}
-    for i in range(args.warmup):
-        step_resident(i, stats)
-    stats = {"score_ms": 0.0, "cells": 0.0, "hits": 0, "steps": 0}
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = dev.launch_count()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(args.warmup, nsteps_total):
-        step_resident(i, stats)
-    e1.record(stream)
-    barrier()
-    elapsed_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.summary()
-    launches = dev.launch_count() - launches0
-    total_cells = sum_over_ranks(stats["cells"])
-    score_ms_max = max_over_ranks(stats["score_ms"])
-
-    # ---- phase 2: end to end through the public API with host buffers ("e2e") ----
-    pinned = []
-    for i in range(nsteps_total):
-        sym = torch.from_numpy(np.concatenate(reads[i * R:(i + 1) * R])).pin_memory()
-        pinned.append(sym)
-    offs = np.arange(R + 1, dtype=np.int64) * L
-    h2d = d2h = 0
-
-    def step_e2e(i):
-        nonlocal h2d, d2h
-        dev.set_reads_packed(pinned[i].numpy(), offs)
-        dev.score_grid(0, nprof, 0, R, True, False)
-        nul, alt = dev.scores_fetch(nprof * R)
-        pr = hit_pairs(0)
-        nst = 0
-        if len(pr):
-            _, off, _ids, _sz = dev.trace_pairs_flat(pr, True, False)
-            nst = int(off[-1])
-        h2d = (R * L + 3) // 4 + R * 12 + len(pr) * 16
-        d2h = nprof * R * 8 + len(pr) * 8 + nst * 3
-        return float(nul[0]) + float(alt[-1])
-
-    for i in range(args.warmup):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.warmup, nsteps_total):
-        step_e2e(i)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    # ---- phase 4: end to end through the reference API ("e2e"), one process driving all N GPUs ----
+    plugin = None
+    small = {}
+    if world > 1:
+        dist.barrier(group=cpu_group)  # every rank has released its GPU memory
+    if rank == 0 and not args.no_plugin:
+        try:
+            plugin = plugin_leg(args, world, sizes, pool, nodes_of, reads, R, nsteps_total)
+        except Exception as e:  # report, do not lose the measured legs
+            plugin = {"unavailable": f"{type(e).__name__}: {e}"}
+        if world == 1:
+            try:
+                small = small_config_legs(args, pool)
+            except Exception as e:
+                small = {"unavailable": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        dist.barrier(group=cpu_group)
 
     if rank == 0:
-        gcups = total_cells / (elapsed_ms * 1e-3) / 1e9
-        e2e_gcups = total_cells / e2e_s / 1e9
-        reads_per_s = args.steps * R / (elapsed_ms * 1e-3)
-        # roofline of the dominant kernel (score pass): algorithmic fp32 ops / its measured device time
-        try:
-            peak = dev.alu_peak(0)
-            peak_src = "measured here: FADD+FMNMX 1:1 issue-rate microbenchmark (dcpgpu_alu_peak mode 0)"
-        except Exception:
-            peak = 148 * 128 * 1.965e9 / 1e12
-            peak_src = "fallback: nominal 148 SM x 128 lanes x 1.965 GHz"
-        achieved = OPS_PER_CELL * stats["cells"] / (stats["score_ms"] * 1e-3) / 1e12
-        # DRAM bytes of one step's score pass, ncu capture of this workload (default sizes, one GPU)
+        gcups = v["total_cells"] / (v["ms"] * 1e-3) / 1e9
+        clocks = v["clocks"]
+        # roofline of the dominant kernels (score pass of the first windows): 33 fp32 ops per cell over their
+        # device time, against the issue ceiling (one lane-op per lane and clock at the sampled SM clock)
+        mhz = clocks.get("sm_mhz") or 1965.0
+        nominal = 148 * 128 * mhz * 1e6 / 1e12
+        achieved = OPS_PER_CELL * v["grid_cells"] / (v["score_ms"] * 1e-3) / 1e12
         traffic_bytes = measured_traffic() if (world == 1 and args.profiles == 20000 and args.reads_per_step == 96
                                                and args.read_len == 2000) else None
+        mix = peaks.get("fadd_vimnmx3_2to1")
+        e2e_cabi = {"value": c["total_cells"] / c["wall_s"] / 1e9, "unit": "GCUPS",
+                    "h2d_bytes_per_step": int(c["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(c["d2h_bytes"] / args.steps),
+                    "reads_per_s": args.steps * R / c["wall_s"],
+                    "api": "dcpgpu_reads_set + score_grid + scores_fetch + hits_fetch + trace_pairs + match_build (libdcpgpu.so), "
+                           "rank 0's bytes, wall clock, max over ranks"}
+        if plugin and "value" in plugin:
+            e2e = dict(plugin)
+            if plugin["profiles"] == len(sizes):
+                e2e["same_cells_as_value"] = bool(plugin["cells"] == v["total_cells"])
+                e2e["same_lrt_windows_as_value"] = bool(plugin["lrt_windows"] == int(v["total_hits"]))
+        else:
+            e2e = dict(e2e_cabi)
+            e2e["note"] = "dcp_scan_run leg " + (plugin or {}).get("unavailable", "skipped (--no-plugin)") + "; this is the C ABI leg"
         line = {
             "metric": "GCUPS (nt x node DP cells/s), Pfam-scale scan", "value": gcups, "unit": "GCUPS",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v["ms"] / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, sizes, [int(c) for c in cuts]),
-            "reads_per_s": reads_per_s,
+            "config": workload_config(args, sizes, [int(x) for x in cuts]),
+            "reads_per_s": args.steps * R / (v["ms"] * 1e-3),
             "clocks": clocks,
-            "e2e": {"value": e2e_gcups, "unit": "GCUPS", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "reads_per_s": args.steps * R / e2e_s},
-            "gpu_launches": int(launches),
+            "e2e": e2e,
+            "e2e_cabi": e2e_cabi,
+            "gpu_launches": int(v["launches"]),
             "roofline": {"bound": "fp32-alu (non-tensor add/min issue; not hbm, not tensor)", "achieved": achieved,
-                         "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic_bytes,
-                         "kernel": "score pass = score_sub_kernel<Q,G> (K<=128) + score_reg_kernel<Q,1> (K<=256) + score_lstrip/subtail_kernel over 256-node segments (K<=2048, exact redo of failed speculation) + generic_kernel<false> (rest), rank 0",
-                         "ops_per_cell": OPS_PER_CELL, "kernel_gcups": stats["cells"] / (stats["score_ms"] * 1e-3) / 1e9,
-                         "kernel_ms_per_step": stats["score_ms"] / args.steps, "peak_source": peak_src,
+                         "peak": nominal, "unit": "TFLOP/s", "frac": achieved / nominal, "traffic": traffic_bytes,
+                         "peak_source": f"issue ceiling: 148 SMs x 128 lanes x {mhz:.0f} MHz (SM clock sampled under load), one "
+                                        "fp32 add/min per lane and clock; MEASURED_PEAKS.json has no ALU entry",
+                         "peak_measured_mix": mix, "frac_of_measured_mix": (achieved / mix) if mix else None,
+                         "peak_measured_mix_source": "dcpgpu_alu_peak mode 6 on this GPU: FADD + three-input integer min 2:1 "
+                                                     "(the row's own mix; a min3 counts as two of the 33 ops)",
+                         "alu_probe": peaks,
+                         "kernel": "score pass of the first windows = score_row_kernel<Q,SEG,MODE> (row_kernel.cuh): whole "
+                                   "profiles of <= 256 nodes (SEG 32/16/8/4), 256-node segments + tail of larger ones "
+                                   "(speculative B, exact redo by score_reg_kernel<Q,W>), generic_kernel<false> for the rest; rank 0",
+                         "ops_per_cell": OPS_PER_CELL, "kernel_gcups": v["grid_cells"] / (v["score_ms"] * 1e-3) / 1e9,
+                         "kernel_ms_per_step": v["score_ms"] / args.steps,
                          "hbm_gbs_measured": _measured_peaks().get("hbm_gbs")},
-            "hits_per_step": stats["hits"] / args.steps, "path_steps_per_step": stats["steps"] / args.steps,
-            "db_build_s": t_build, "db_bytes_rank0": dev.profile_bytes, "score_ms_max_rank": score_ms_max / args.steps,
+            "hits_per_step": v["hits"] / args.steps, "path_steps_per_step": v["steps"] / args.steps,
+            "later_windows_per_step": v["later_windows"] / args.steps, "multi_window_profiles_rank0": multi_window,
+            "db_build_s": t_build, "db_bytes_rank0": db_bytes, "score_ms_max_rank": score_ms_max / args.steps,
         }
+        if strong:
+            line["strong"] = strong
+        if small:
+            line["configs"] = small
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline_record(args, sizes, pool)
+                line["cpu_baseline"] = cpu_baseline_record(args, sizes, pool, small)
             except Exception as e:  # the checker is optional for the measured arm
                 line["cpu_baseline"] = {"value": None, "unit": "GCUPS", "cores": os.cpu_count(), "kind": "reference",
                                         "sample": f"unavailable: {e}"}
         print(json.dumps(line), flush=True)
-    dev.close()
     if world > 1:
         dist.destroy_process_group()
 

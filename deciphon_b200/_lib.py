@@ -40,6 +40,7 @@ SYMBOLS = [
     ("dcpgpu_last_kernel_ms", _f32, [_vp]),
     ("dcpgpu_last_redo", _i64, [_vp]),
     ("dcpgpu_launch_count", _i64, [_vp]),
+    ("dcpgpu_counter", C.c_double, [_vp, C.c_int]),
     ("dcpgpu_alu_peak", C.c_int, [_vp, C.c_int, C.POINTER(C.c_double)]),
     ("dcpgpu_frame_tables", C.c_int, [_vp, _i32, _vp, _vp, _f32, _vp]),
     ("dcpgpu_profile_set_decoder", C.c_int, [_vp, _i32, _vp, _vp, _vp, C.c_char_p]),

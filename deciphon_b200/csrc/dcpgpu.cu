@@ -145,6 +145,8 @@ struct dcpgpu_ctx
   bool timed = false;
   double last_cells = 0;
   int64_t launches = 0; // cumulative count of kernels this library launched
+  int64_t h2d_bytes = 0, d2h_bytes = 0; // cumulative bytes of the copies this library issued
+  double total_cells = 0; // cumulative DP cells over the score passes (dcpgpu_counter)
 
   // trace pass state (buffers grow on demand and are reused across calls)
   std::vector<Pair> t_pairs;
@@ -203,6 +205,15 @@ int fail(dcpgpu_ctx *c, int code, char const *what)
 {
   if (c) c->err = what;
   return code;
+}
+
+// every host<->device copy of the library goes through here so that dcpgpu_counter can report them
+inline cudaError_t counted_copy(dcpgpu_ctx *ctx, void *dst, void const *src, size_t bytes, cudaMemcpyKind kind,
+                                cudaStream_t st)
+{
+  if (kind == cudaMemcpyHostToDevice) ctx->h2d_bytes += (int64_t)bytes;
+  else if (kind == cudaMemcpyDeviceToHost) ctx->d2h_bytes += (int64_t)bytes;
+  return cudaMemcpyAsync(dst, src, bytes, kind, st);
 }
 
 #define CU(call)                                                                                 \
@@ -369,7 +380,7 @@ int ensure_xt(dcpgpu_ctx *ctx, uint32_t flags, int maxlen)
   if (ctx->d_xt[f]) CU(cudaFree(ctx->d_xt[f]));
   ctx->d_xt[f] = nullptr;
   CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_xt[f]), h.size() * sizeof(float)));
-  CU(cudaMemcpyAsync(ctx->d_xt[f], h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_xt[f], h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->xt_len[f] = n;
   return 0;
@@ -387,18 +398,18 @@ int sync_profiles(dcpgpu_ctx *ctx)
     CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_profiles), cap * sizeof(ProfileDesc)));
     ctx->d_profiles_cap = cap;
   }
-  CU(cudaMemcpyAsync(ctx->d_profiles, ctx->h_profiles.data(), n * sizeof(ProfileDesc),
+  CU(counted_copy(ctx, ctx->d_profiles, ctx->h_profiles.data(), n * sizeof(ProfileDesc),
                      cudaMemcpyHostToDevice, ctx->stream));
   int rc;
   ctx->h_decoders.resize(n, DecoderDesc{nullptr, {0}});
   if ((rc = ensure(ctx, ctx->d_decoders, ctx->d_decoders_cap, n))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_decoders, ctx->h_decoders.data(), n * sizeof(DecoderDesc), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_decoders, ctx->h_decoders.data(), n * sizeof(DecoderDesc), cudaMemcpyHostToDevice, ctx->stream));
   if ((rc = ensure(ctx, ctx->d_seg_first, ctx->d_seg_first_cap, n))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_seg_first, ctx->h_seg_first.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_seg_first, ctx->h_seg_first.data(), n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   if (!ctx->h_segs.empty())
   {
     if ((rc = ensure(ctx, ctx->d_segs, ctx->d_segs_cap, ctx->h_segs.size()))) return rc;
-    CU(cudaMemcpyAsync(ctx->d_segs, ctx->h_segs.data(), ctx->h_segs.size() * sizeof(ProfileDesc),
+    CU(counted_copy(ctx, ctx->d_segs, ctx->h_segs.data(), ctx->h_segs.size() * sizeof(ProfileDesc),
                        cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
@@ -605,9 +616,9 @@ int prepare_segments(dcpgpu_ctx *ctx, bool grid, std::vector<std::pair<int, long
   if ((rc = ensure(ctx, ctx->d_seg_list, ctx->seg_list_cap, m))) return rc;
   if ((rc = ensure(ctx, ctx->d_seg_order, ctx->seg_order_cap, m))) return rc;
   if ((rc = ensure(ctx, ctx->d_seg_colmap, ctx->seg_colmap_cap, m))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_seg_list, list.data(), m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_seg_order, order.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_seg_colmap, colmap.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_seg_list, list.data(), m * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_seg_order, order.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_seg_colmap, colmap.data(), m * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // the vectors are locals
   return 0;
 }
@@ -679,12 +690,12 @@ template <class F>
 int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
 {
   unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, ctx->d_counters + SLOT_NREDO, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, &n, ctx->d_counters + SLOT_NREDO, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->last_redo = (int64_t)n;
   if (n == 0) return 0;
   std::vector<long long> redo((size_t)n);
-  CU(cudaMemcpyAsync(redo.data(), ctx->d_redo, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, redo.data(), ctx->d_redo, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   std::sort(redo.begin(), redo.end());
   std::vector<Pair> rp((size_t)n);
@@ -710,9 +721,9 @@ int redo_exact(dcpgpu_ctx *ctx, uint32_t flags, F &&to_pair)
   if ((rc = ensure(ctx, ctx->d_redo_pairs, ctx->redo_pairs_cap, (size_t)n))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo_order, ctx->redo_order_cap, (size_t)n))) return rc;
   if ((rc = ensure(ctx, ctx->d_redo_out, ctx->redo_out_cap, (size_t)n))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_redo_pairs, rp.data(), (size_t)n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_redo_order, order.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_redo_out, out_index.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_redo_pairs, rp.data(), (size_t)n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_redo_order, order.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_redo_out, out_index.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_counters, 0, NCLASS * sizeof(unsigned long long), ctx->stream));
   if ((rc = fork_streams(ctx))) return rc;
   for (int c = 9; c <= 20; ++c)
@@ -859,6 +870,7 @@ static int run_alu_peak(dcpgpu_ctx *ctx, double *tops)
   if (MODE == 3) per_iter = 32.0;         // 16 FMNMX3
   if (MODE == 4) per_iter = 32.0;         // 16 FADD2
   if (MODE == 5) per_iter = 32.0;         // 16 FADD + 8 FMNMX3
+  if (MODE == 6) per_iter = 32.0;         // 16 FADD + 8 VIMNMX3
   double const ops = per_iter * iters * (double)blocks * threads;
   *tops = ops / (best * 1e-3) / 1e12;
   return 0;
@@ -1060,8 +1072,8 @@ int dcpgpu_pool_add(dcpgpu_ctx *ctx, int nnodes, float const *emission, float co
   }
   ctx->pool.push_back(b);
   ctx->pool_nodes += nnodes;
-  CU(cudaMemcpyAsync(b.em, emission, eb, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(b.trans, trans, tb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, b.em, emission, eb, cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, b.trans, trans, tb, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (first_node_id) *first_node_id = b.first;
   return 0;
@@ -1132,10 +1144,10 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
   size_t const o_bg = o_nul + (size_t)NCODES * sizeof(float);
   size_t const total = o_bg + (size_t)NCODES * sizeof(float);
   if ((rc = ensure(ctx, ctx->d_stage, ctx->d_stage_cap, total))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_stage + o_refs, refs.data(), (size_t)K * sizeof(NodeRef), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_stage + o_bm, BMk, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_stage + o_nul, null_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_stage + o_bg, bg_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_stage + o_refs, refs.data(), (size_t)K * sizeof(NodeRef), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_stage + o_bm, BMk, (size_t)K * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_stage + o_nul, null_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_stage + o_bg, bg_emission, NCODES * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
 
   NodeRef const *drefs = reinterpret_cast<NodeRef const *>(ctx->d_stage + o_refs);
   int const VL = d.VL;
@@ -1181,7 +1193,7 @@ int dcpgpu_profile_add(dcpgpu_ctx *ctx, int K, int64_t const *node_ids, int64_t 
     }
   }
   int h_bad = 0;
-  CU(cudaMemcpyAsync(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, &h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   ctx->launches += 3;
   // the staging buffer is reused by the next call: finish the pack first
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1267,7 +1279,7 @@ int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int6
   CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_words), words.size() * sizeof(uint32_t)));
   CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_seq_word), std::max<size_t>(1, seq_word.size()) * sizeof(long long)));
   CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_seq_len), std::max<size_t>(1, seq_len.size()) * sizeof(int)));
-  CU(cudaMemcpyAsync(ctx->d_words, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_words, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   {
     long long const nhist = (long long)words.size() * 16 + HIST_SLACK;
     CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_hist), (size_t)nhist * sizeof(uint16_t)));
@@ -1277,8 +1289,8 @@ int dcpgpu_reads_set(dcpgpu_ctx *ctx, int32_t nseq, uint8_t const *symbols, int6
   }
   if (nseq)
   {
-    CU(cudaMemcpyAsync(ctx->d_seq_word, seq_word.data(), seq_word.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->d_seq_len, seq_len.data(), seq_len.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(counted_copy(ctx, ctx->d_seq_word, seq_word.data(), seq_word.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(counted_copy(ctx, ctx->d_seq_len, seq_len.data(), seq_len.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->h_seq_len.swap(seq_len);
@@ -1356,8 +1368,8 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     }
   }
   bool any_strip = false;
-  CU(cudaMemcpyAsync(ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_pairs, pairs, (size_t)npairs * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_order, order.data(), (size_t)npairs * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
 
   if ((rc = fork_streams(ctx))) return rc;
   if (seg_ok)
@@ -1403,6 +1415,7 @@ int dcpgpu_score_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       })))
     return rc;
   ctx->last_cells = cells;
+  ctx->total_cells += cells;
   if ((rc = end_pass(ctx, npairs))) return rc;
   return dcpgpu_scores_fetch(ctx, npairs, null_cost, alt_cost);
 }
@@ -1466,7 +1479,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
     }
   }
   bool any_strip = false;
-  CU(cudaMemcpyAsync(ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_class_profiles, flat.data(), flat.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // flat is a local
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
 
@@ -1520,6 +1533,7 @@ int dcpgpu_score_grid(dcpgpu_ctx *ctx, int32_t prof0, int32_t prof1, int32_t seq
       })))
     return rc;
   ctx->last_cells = cells;
+  ctx->total_cells += cells;
   return end_pass(ctx, (int64_t)npairs);
 }
 
@@ -1530,7 +1544,7 @@ int dcpgpu_scores_fetch(dcpgpu_ctx *ctx, int64_t npairs, float *null_cost, float
   if (npairs && (null_cost || alt_cost))
   {
     std::vector<float2> h((size_t)npairs);
-    CU(cudaMemcpyAsync(h.data(), ctx->d_out, (size_t)npairs * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(counted_copy(ctx, h.data(), ctx->d_out, (size_t)npairs * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int64_t i = 0; i < npairs; ++i)
     {
@@ -1548,7 +1562,7 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
   if (!ctx || cap < 0 || !nhits) return fail(ctx, DCPGPU_EINVAL, "hits_fetch: bad argument");
   CU(cudaSetDevice(ctx->device));
   unsigned long long n = 0;
-  CU(cudaMemcpyAsync(&n, ctx->d_counters + SLOT_NHITS, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, &n, ctx->d_counters + SLOT_NHITS, sizeof n, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   *nhits = (int64_t)n;
   if (!hit_index || cap == 0 || n == 0) return 0;
@@ -1561,7 +1575,7 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
                                                                        (long long)n, d_idx);
   ctx->launches += 1;
   std::vector<long long> h((size_t)n);
-  cudaError_t e = cudaMemcpyAsync(h.data(), d_idx, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
+  cudaError_t e = counted_copy(ctx, h.data(), d_idx, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
   if (e != cudaSuccess) return fail_cuda(ctx, e, "hits_fetch");
   std::sort(h.begin(), h.end());
@@ -1573,6 +1587,19 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
 double dcpgpu_last_cells(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_cells : 0.0; }
 int64_t dcpgpu_last_redo(dcpgpu_ctx const *ctx) { return ctx ? ctx->last_redo : 0; }
 int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx) { return ctx ? ctx->launches : 0; }
+
+double dcpgpu_counter(dcpgpu_ctx const *ctx, int what)
+{
+  if (!ctx) return 0.0;
+  switch (what)
+  {
+  case 0: return (double)ctx->h2d_bytes;
+  case 1: return (double)ctx->d2h_bytes;
+  case 2: return (double)ctx->launches;
+  case 3: return ctx->total_cells;
+  default: return 0.0;
+  }
+}
 
 float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx)
 {
@@ -1632,11 +1659,11 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     if ((rc = ensure(ctx, ctx->d_lz_ids, ctx->lz_ids_cap, (size_t)slot_off[n]))) return rc;
     if ((rc = ensure(ctx, ctx->d_lz_sz, ctx->lz_sz_cap, (size_t)slot_off[n]))) return rc;
   }
-  CU(cudaMemcpyAsync(ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_counters + SLOT_OVERFLOW, 0, sizeof(unsigned long long), ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_tpairs, pairs, n * sizeof(Pair), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_counters + SLOT_TRACE_CUR, 0, 5 * sizeof(unsigned long long), ctx->stream));
 
   // ---- fast route: pairs whose profile runs on a register kernel -------------------------------
@@ -1720,10 +1747,10 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
         gstart.push_back(cn);
         if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, cn))) return rc;
         if ((rc = ensure(ctx, ctx->d_tile_off, ctx->tile_off_cap, tile_off.size()))) return rc;
-        CU(cudaMemcpyAsync(ctx->d_order, sorted.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->d_tile_off, tile_off.data(), tile_off.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(counted_copy(ctx, ctx->d_order, sorted.data() + c0, cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(counted_copy(ctx, ctx->d_tile_off, tile_off.data(), tile_off.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
         // dump offsets are indexed by the item's position in its launch
-        CU(cudaMemcpyAsync(ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(counted_copy(ctx, ctx->d_dump_off, doff.data(), cn * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(ctx->d_counters, 0, NCLASS * sizeof(unsigned long long), ctx->stream));
         if ((rc = fork_streams(ctx))) return rc;
         for (size_t gi = 0; gi + 1 < gstart.size(); ++gi)
@@ -1810,11 +1837,11 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     if (!keep)
     { // a path that outgrew its slot was only counted: give every pair its exact size and redo
       unsigned long long over = 0;
-      CU(cudaMemcpyAsync(&over, ctx->d_counters + SLOT_OVERFLOW, sizeof over, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(counted_copy(ctx, &over, ctx->d_counters + SLOT_OVERFLOW, sizeof over, cudaMemcpyDeviceToHost, ctx->stream));
       CU(cudaStreamSynchronize(ctx->stream));
       if (over)
       {
-        CU(cudaMemcpyAsync(ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(counted_copy(ctx, ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
         for (size_t i = 0; i < n; ++i)
         {
@@ -1823,7 +1850,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
         }
         if ((rc = ensure(ctx, ctx->d_lz_ids, ctx->lz_ids_cap, (size_t)slot_off[n]))) return rc;
         if ((rc = ensure(ctx, ctx->d_lz_sz, ctx->lz_sz_cap, (size_t)slot_off[n]))) return rc;
-        CU(cudaMemcpyAsync(ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+        CU(counted_copy(ctx, ctx->d_lz_off, slot_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemsetAsync(ctx->d_counters + SLOT_OVERFLOW, 0, sizeof(unsigned long long), ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream)); // slot_off is re-read by nothing after this, but keep it simple
         if ((rc = run_fast())) return rc;
@@ -1854,7 +1881,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   if (!torder.empty())
   {
     if ((rc = ensure(ctx, ctx->d_order, ctx->order_cap, torder.size()))) return rc;
-    CU(cudaMemcpyAsync(ctx->d_order, torder.data(), torder.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+    CU(counted_copy(ctx, ctx->d_order, torder.data(), torder.size() * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   }
 
   unsigned tgrid[4] = {0, 0, 0, 0};
@@ -1902,8 +1929,8 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   }
 
   std::vector<float2> h(n);
-  CU(cudaMemcpyAsync(h.data(), ctx->d_tout, n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, h.data(), ctx->d_tout, n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n; ++i)
   {
@@ -1930,7 +1957,7 @@ static int compact_steps(dcpgpu_ctx *ctx, std::vector<long long> *off_out)
   if ((rc = ensure(ctx, ctx->d_step_sz, ctx->step_sz_cap, total))) return rc;
   uint16_t *d_ids = ctx->d_step_ids;
   uint8_t *d_sz = ctx->d_step_sz;
-  CU(cudaMemcpyAsync(ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_step_off, off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // off is a local
   if (ctx->t_node_off[n] > 0)
   { // pairs traced through a trellis: second back-walk, in path order
@@ -1985,15 +2012,15 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
   for (size_t i = 0; i < n && compact; ++i) compact = offsets[i] == offsets[0] + off[i];
   if (compact)
   {
-    CU(cudaMemcpyAsync(state_ids + offsets[0], d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(seqsizes + offsets[0], d_sz, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(counted_copy(ctx, state_ids + offsets[0], d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(counted_copy(ctx, seqsizes + offsets[0], d_sz, total, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return 0;
   }
   std::vector<uint16_t> h_ids(total);
   std::vector<uint8_t> h_sz(total);
-  CU(cudaMemcpyAsync(h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, h_ids.data(), d_ids, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, h_sz.data(), d_sz, total, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   for (size_t i = 0; i < n; ++i)
   {
@@ -2012,9 +2039,9 @@ int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t 
   if (nx == 0) return fail(ctx, DCPGPU_ESTATE, "trace_trellis: trace_pairs ran without DCPGPU_KEEP_TRELLIS");
   size_t const nn = (size_t)(ctx->t_node_off[(size_t)i + 1] - ctx->t_node_off[(size_t)i]);
   if (xnodes)
-    CU(cudaMemcpyAsync(xnodes, ctx->d_xnodes + ctx->t_xnode_off[(size_t)i], nx * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(counted_copy(ctx, xnodes, ctx->d_xnodes + ctx->t_xnode_off[(size_t)i], nx * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   if (nodes)
-    CU(cudaMemcpyAsync(nodes, ctx->d_nodes + ctx->t_node_off[(size_t)i], nn * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(counted_copy(ctx, nodes, ctx->d_nodes + ctx->t_node_off[(size_t)i], nn * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -2031,6 +2058,7 @@ int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s)
   case 3: return run_alu_peak<3>(ctx, tera_ops_per_s);
   case 4: return run_alu_peak<4>(ctx, tera_ops_per_s);
   case 5: return run_alu_peak<5>(ctx, tera_ops_per_s);
+  case 6: return run_alu_peak<6>(ctx, tera_ops_per_s);
   default: return fail(ctx, DCPGPU_EINVAL, "alu_peak: bad mode");
   }
 }
@@ -2047,9 +2075,9 @@ int dcpgpu_profile_set_decoder(dcpgpu_ctx *ctx, int32_t profile, float const *no
   int rc;
   if ((rc = arena_alloc(ctx, (size_t)(K + 2) * DIST_FLOATS * sizeof(float), &mem))) return rc;
   float *d = static_cast<float *>(mem);
-  CU(cudaMemcpyAsync(d, node_dists, (size_t)K * DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(d + (size_t)K * DIST_FLOATS, null_dist, DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(d + (size_t)(K + 1) * DIST_FLOATS, bg_dist, DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, d, node_dists, (size_t)K * DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, d + (size_t)K * DIST_FLOATS, null_dist, DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, d + (size_t)(K + 1) * DIST_FLOATS, bg_dist, DIST_FLOATS * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream)); // the caller's buffers may be reused right away
   ctx->h_decoders.resize(ctx->h_profiles.size(), DecoderDesc{nullptr, {0}});
   DecoderDesc &dd = ctx->h_decoders[(size_t)profile];
@@ -2097,6 +2125,7 @@ int dcpgpu_match_build(dcpgpu_ctx *ctx, float epsilon, int is_rna, int32_t *hit,
   a.reads = reads_view(ctx);
   a.eps = (double)epsilon;
   a.is_rna = is_rna;
+  a.extent_only = text_off ? 0 : 1;
   a.hit = ctx->d_m_hit;
   a.hit_start = ctx->d_m_start;
   a.hit_stop = ctx->d_m_stop;
@@ -2114,11 +2143,11 @@ int dcpgpu_match_build(dcpgpu_ctx *ctx, float epsilon, int is_rna, int32_t *hit,
   std::vector<long long> len(n);
   std::vector<int> h_hit(n), h_start(n), h_stop(n);
   int bad = 0;
-  CU(cudaMemcpyAsync(len.data(), ctx->d_m_len, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h_hit.data(), ctx->d_m_hit, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h_start.data(), ctx->d_m_start, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(h_stop.data(), ctx->d_m_stop, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaMemcpyAsync(&bad, ctx->d_m_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, len.data(), ctx->d_m_len, n * sizeof(long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, h_hit.data(), ctx->d_m_hit, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, h_start.data(), ctx->d_m_start, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, h_stop.data(), ctx->d_m_stop, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, &bad, ctx->d_m_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   if (bad) return fail(ctx, DCPGPU_EDECODE, "match_build: a fragment could not be decoded into a codon (or no decoder tables)");
   for (size_t i = 0; i < n; ++i)
@@ -2130,8 +2159,9 @@ int dcpgpu_match_build(dcpgpu_ctx *ctx, float epsilon, int is_rna, int32_t *hit,
     if (text_off) text_off[i + 1] = (int64_t)ctx->m_text_off[i + 1];
   }
   size_t const bytes = (size_t)ctx->m_text_off[n];
+  if (a.extent_only) return 0;
   if ((rc = ensure(ctx, ctx->d_m_text, ctx->m_text_cap, bytes + 1))) return rc;
-  CU(cudaMemcpyAsync(ctx->d_m_off, ctx->m_text_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, ctx->d_m_off, ctx->m_text_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   a.text = ctx->d_m_text;
   match_kernel<true><<<grid, 32 * MATCH_WARPS, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
@@ -2146,7 +2176,7 @@ int dcpgpu_match_fetch(dcpgpu_ctx *ctx, char *text)
   if (bytes == 0) return 0;
   if (!text) return fail(ctx, DCPGPU_EINVAL, "match_fetch: bad argument");
   CU(cudaSetDevice(ctx->device));
-  CU(cudaMemcpyAsync(text, ctx->d_m_text, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, text, ctx->d_m_text, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
@@ -2164,13 +2194,13 @@ int dcpgpu_frame_tables(dcpgpu_ctx *ctx, int32_t nstates, float const *nuclt_lpr
   int rc;
   if ((rc = ensure(ctx, ctx->d_scratch, ctx->scratch_cap, in_floats + out_floats))) return rc;
   float *d_nuclt = ctx->d_scratch, *d_marg = d_nuclt + n * 4, *d_out = d_marg + n * 125;
-  CU(cudaMemcpyAsync(d_nuclt, nuclt_lprobs, n * 4 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(d_marg, codon_marg_lprobs, n * 125 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, d_nuclt, nuclt_lprobs, n * 4 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(counted_copy(ctx, d_marg, codon_marg_lprobs, n * 125 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   FrameArgs a{d_nuclt, d_marg, d_out, epsilon, nstates};
   frame_table_kernel<<<(unsigned)nstates, 256, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches += 1;
-  CU(cudaMemcpyAsync(emission, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(counted_copy(ctx, emission, d_out, out_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -641,6 +641,14 @@ __global__ void __launch_bounds__(256) alu_peak_kernel(float *out, int iters, fl
       if (MODE == 2) { DCP_FMIN(a[j], a[j], b[j]); DCP_FMIN(c[j], c[j], b[j]); }
       if (MODE == 3) { DCP_FMIN3(a[j], a[j], b[j], c[j]); DCP_FMIN3(b[j], b[j], c[j], a[j]); }
       if (MODE == 5) { DCP_FADD(a[j], a[j], b[j]); DCP_FADD(b[j], b[j], c[j]); DCP_FMIN3(c[j], c[j], a[j], b[j]); }
+      if (MODE == 6)
+      { // the score row's own mix: two FADD per three-input INTEGER min (VIMNMX3, row_kernel.cuh)
+        DCP_FADD(a[j], a[j], b[j]);
+        DCP_FADD(b[j], b[j], c[j]);
+        int m;
+        asm volatile("min.s32 %0, %1, %2;" : "=r"(m) : "r"(__float_as_int(c[j])), "r"(__float_as_int(a[j])));
+        c[j] = __int_as_float(min(m, __float_as_int(b[j])));
+      }
     }
     if (MODE == 4)
     {

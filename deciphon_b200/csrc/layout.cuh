@@ -54,6 +54,7 @@ inline void layout_shape(int K, int *Q, int *W, int *VL, bool subwarp = true)
     int vl = K <= 4 * MAXQ_REG ? 4 : K <= 8 * MAXQ_REG ? 8 : 16;
     int q = (K + vl - 1) / vl;
     if (q < 5) q = 5;
+    if (q == 7) q = 8; // measured: the 4+2+1 chunk row (three loads per code) is slower than Q = 8 padded
     *W = 1;
     *VL = vl;
     *Q = q;
@@ -64,6 +65,7 @@ inline void layout_shape(int K, int *Q, int *W, int *VL, bool subwarp = true)
   *W = w;
   *VL = 32 * w;
   *Q = (K + 32 * w - 1) / (32 * w);
+  if (w == 1 && *Q == 7) *Q = 8; // same measurement (K = 224: 27.8 ms at Q = 7, 26.8 ms at Q = 8)
 }
 
 // One (window, profile) unit of work; mirrors dcpgpu_pair.

@@ -38,6 +38,7 @@ struct MatchArgs
   ReadsView reads;
   double eps;
   int is_rna;
+  int extent_only; // stop after the hit extents (no decode tables needed)
   // per pair
   int *hit;        // 1: the path has a B..E segment
   int *hit_start;  // window-relative (thread.c:140-158)
@@ -161,9 +162,9 @@ __global__ void __launch_bounds__(32 * MATCH_WARPS) match_kernel(MatchArgs a)
       a.hit_stop[pi] = pos_e;
       a.seg_begin[pi] = b;
       a.seg_end[pi] = end;
-      if (!hit) a.text_len[pi] = 0;
+      if (!hit || a.extent_only) a.text_len[pi] = 0;
     }
-    if (!hit) return;
+    if (!hit || a.extent_only) return;
   }
   else
   {

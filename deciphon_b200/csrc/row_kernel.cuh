@@ -356,14 +356,18 @@ __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EmRows<Q, SEG
   }
 }
 
-template <int Q, int SEG>
+// Resident CTAs per SM asked of ptxas.  Q = 6 whole-warp: 168 registers with 52 bytes of spills and
+// 12 warps/SM beat 209 registers and 8 warps/SM (K = 192: 516 -> 558 GCUPS); the same trade loses
+// for Q = 7, 8 (hundreds of spill bytes) and for every sub-warp shape (r2_qp_mb.log).
+template <int Q, int SEG, int MODE, bool DUMP>
 constexpr int row_min_blocks()
 {
+  if (Q == 6 && SEG == 32 && MODE == ROW_WHOLE && !DUMP) return 3;
   return Q >= 6 ? 2 : Q >= 4 ? 3 : Q == 3 ? 4 : Q == 2 ? 5 : 6;
 }
 
 template <int Q, int SEG, int MODE, bool DUMP = false>
-__global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG>()) score_row_kernel(StripArgs a)
+__global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, DUMP>()) score_row_kernel(StripArgs a)
 {
   constexpr int G = 32 / SEG;
   static_assert(!DUMP || MODE == ROW_WHOLE, "the value dump runs on whole profiles");

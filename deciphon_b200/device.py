@@ -203,6 +203,7 @@ class Device:
         self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs),
                                            flags_of(multi_hits, hmmer3_compat, keep_trellis),
                                            _ptr(alt), _ptr(nsteps)))
+        self._last_traced = n
         off = np.zeros(n + 1, dtype=np.int64)
         off[1:] = np.cumsum(nsteps)
         ids = np.zeros(max(int(off[-1]), 1), dtype=np.uint16)
@@ -222,6 +223,7 @@ class Device:
         self._check(lib.dcpgpu_trace_pairs(self._h, n, _ptr(pairs),
                                            flags_of(multi_hits, hmmer3_compat, keep_trellis),
                                            _ptr(alt), _ptr(nsteps)))
+        self._last_traced = n
         off = np.zeros(n + 1, dtype=np.int64)
         off[1:] = np.cumsum(nsteps)
         ids = np.zeros(max(int(off[-1]), 1), dtype=np.uint16)
@@ -229,6 +231,38 @@ class Device:
         self._check(lib.dcpgpu_trace_fetch(self._h, _ptr(off), _ptr(ids), _ptr(sz)))
         paths = [(ids[off[i]:off[i + 1]].copy(), sz[off[i]:off[i + 1]].copy()) for i in range(n)]
         return alt, paths
+
+    # -- post-processing of the traced paths on the device -----------------------------------
+    def set_decoder(self, profile: int, node_dists, null_dist, bg_dist, gencode64: str):
+        """Decode tables of a resident profile: node_dists f32[K,129], null/bg f32[129] (4 base
+        log-probs + 125 codon marginals) and the 64 amino letters of its genetic code (TCAG order)."""
+        nd = np.ascontiguousarray(node_dists, dtype=np.float32)
+        nu = np.ascontiguousarray(null_dist, dtype=np.float32)
+        bg = np.ascontiguousarray(bg_dist, dtype=np.float32)
+        assert nd.shape[1] == 129 and nu.size == 129 and bg.size == 129 and len(gencode64) == 64
+        self._check(lib.dcpgpu_profile_set_decoder(self._h, profile, _ptr(nd), _ptr(nu), _ptr(bg), gencode64.encode()))
+
+    def match_build(self, epsilon: float = 0.01, is_rna: bool = False, want_text: bool = False):
+        """Hit flag and window-relative extent [start, stop) of every pair of the preceding trace
+        pass (thread.c:130-166); with want_text also the bytes of each row's match column."""
+        n = self._last_traced
+        hit = np.zeros(n, dtype=np.int32)
+        hs = np.zeros(n, dtype=np.int32)
+        he = np.zeros(n, dtype=np.int32)
+        off = np.zeros(n + 1, dtype=np.int64)
+        self._check(lib.dcpgpu_match_build(self._h, float(epsilon), int(is_rna), _ptr(hit), _ptr(hs), _ptr(he),
+                                           _ptr(off) if want_text else None))
+        if not want_text:
+            return hit, hs, he
+        text = np.zeros(int(off[-1]) + 1, dtype=np.uint8)
+        self._check(lib.dcpgpu_match_fetch(self._h, _ptr(text)))
+        raw = text.tobytes()
+        return hit, hs, he, [raw[off[i]:off[i + 1]].decode() for i in range(n)]
+
+    def counters(self) -> dict:
+        """Cumulative H2D / D2H bytes, kernel launches and DP cells of this context."""
+        names = ("h2d_bytes", "d2h_bytes", "launches", "cells")
+        return {k: float(lib.dcpgpu_counter(self._h, i)) for i, k in enumerate(names)}
 
     def trace_trellis(self, i: int, length: int, K: int):
         xn = np.zeros(length + 1, dtype=np.uint32)

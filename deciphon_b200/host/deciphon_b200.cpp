@@ -91,7 +91,8 @@ struct dcp_scan
   void *userdata = nullptr;
   std::atomic<bool> interrupted{false};
   std::atomic<int> done_proteins{0};
-  double chunk_cells = 4e10; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
+  std::atomic<long> windows{0}, lrt_windows{0}; // cumulative: windows scored / with lrt >= 0 (dcpb200_scan_counter)
+  double chunk_cells = 2e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
 };
 
 namespace {
@@ -560,6 +561,16 @@ int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size
 
 int dcpb200_scan_num_gpus(struct dcp_scan const *x) { return x ? (int)x->shards.size() : 0; }
 
+double dcpb200_scan_counter(struct dcp_scan const *x, int what)
+{
+  if (!x) return 0;
+  if (what == 4) return (double)x->windows;
+  if (what == 5) return (double)x->lrt_windows;
+  double v = 0;
+  for (auto const &sh : x->shards) v += dcpgpu_counter(sh.gpu, what);
+  return v;
+}
+
 void dcp_scan_interrupt(struct dcp_scan *x)
 {
   if (x) x->interrupted = true;
@@ -663,6 +674,8 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
     if ((rc = dcpgpu_hits_fetch(gpu, 0, nullptr, &nhits))) return map_gpu_error(rc);
     std::vector<int64_t> hit((size_t)nhits);
     if (nhits && (rc = dcpgpu_hits_fetch(gpu, nhits, hit.data(), &nhits))) return map_gpu_error(rc);
+    x->windows += (long)P * S;
+    x->lrt_windows += (long)nhits;
     std::vector<float> nul0, alt0;
     if (nhits)
     {
@@ -733,6 +746,8 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
         ha2.push_back(altc[i]);
         owner2.push_back(&next[i]);
       }
+      x->windows += (long)wp.size();
+      x->lrt_windows += (long)hp2.size();
       if ((rc = process_hits(hp2, widx2, hn2, ha2, owner2))) return rc;
       active.swap(next);
       if (shard_index == 0 && x->callback) x->callback(x->userdata);

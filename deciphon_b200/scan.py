@@ -39,6 +39,7 @@ SYMBOLS = [
     ("dcp_error_string", C.c_char_p, [C.c_int]),
     ("dcpb200_db_info", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_float)]),
     ("dcpb200_scan_num_gpus", C.c_int, [C.c_void_p]),
+    ("dcpb200_scan_counter", C.c_double, [C.c_void_p, C.c_int]),
 ]
 
 
@@ -136,6 +137,12 @@ class Scan:
     def num_gpus(self) -> int:
         """GPUs (= profile shards) this scan runs on."""
         return lib.dcpb200_scan_num_gpus(self._cscan)
+
+    def counters(self) -> dict:
+        """Cumulative H2D / D2H bytes, kernel launches and DP cells of this scan's GPU contexts, windows
+        scored and windows that passed the lrt gate."""
+        names = ("h2d_bytes", "d2h_bytes", "launches", "cells", "windows", "lrt_windows")
+        return {n: lib.dcpb200_scan_counter(self._cscan, i) for i, n in enumerate(names)}
 
     def free(self):
         if getattr(self, "_cscan", None):

@@ -129,6 +129,9 @@ float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx);
 int64_t dcpgpu_last_redo(dcpgpu_ctx const *ctx);
 /* Cumulative number of kernels this library has launched on the context. */
 int64_t dcpgpu_launch_count(dcpgpu_ctx const *ctx);
+/* Cumulative counters of the context: 0 = bytes copied host -> device, 1 = bytes copied device ->
+ * host, 2 = kernels launched, 3 = DP cells of all score passes. */
+double dcpgpu_counter(dcpgpu_ctx const *ctx, int what);
 
 /* ---- trace pass: viterbi_path + trellis_unzip for the given (hit) pairs -----------------
  * Decides the reference's bit-packed trellis words (trellis.h:12-56) on the device -- only the
@@ -144,9 +147,12 @@ int dcpgpu_trace_fetch(dcpgpu_ctx *ctx, int64_t const *offsets, uint16_t *state_
  * Needs DCPGPU_KEEP_TRELLIS in the flags of the preceding dcpgpu_trace_pairs. */
 int dcpgpu_trace_trellis(dcpgpu_ctx *ctx, int64_t i, uint32_t *xnodes, uint16_t *nodes);
 
-/* Measured non-tensor FP32 issue rate of this GPU in tera lane-operations per second (the
- * roofline denominator of the score kernel).  mode 0: FADD+FMNMX 1:1 (the DP's mix),
- * 1: FADD, 2: FMNMX, 3: FMNMX3 (one op each), 4: FADD2, 5: FADD2+FMNMX3. */
+/* Measured non-tensor FP32 issue rate of this GPU in tera lane-operations per second, a three-input
+ * min and a packed f32x2 add counted as two operations each.  mode 0: FADD+FMNMX 1:1, 1: FADD,
+ * 2: FMNMX, 3: FMNMX3, 4: FADD2, 5: FADD+FMNMX3 2:1, 6: FADD + three-input integer min (VIMNMX3)
+ * 2:1 -- the instruction mix of the score row, the highest add/min rate measured on B200
+ * (tools/alu_probe.cu, profiles/README.md).  The hard issue ceiling, one lane-operation per lane
+ * and clock, is SMs x 128 x clock. */
 int dcpgpu_alu_peak(dcpgpu_ctx *ctx, int mode, double *tera_ops_per_s);
 
 /* ---- match strings: the post-processing of a traced path, on the device --------------------
@@ -159,7 +165,8 @@ int dcpgpu_profile_set_decoder(dcpgpu_ctx *ctx, int32_t profile, float const *no
  * window-relative extent (thread.c:130-166) and the bytes of the row's match column
  * ("<fragment>,<state>,<codon>,<amino>" joined by ';': match.c:66-90, product_thread.c:112-148,
  * codons by the frame-state decoder of decoder.c:38-58).  text_off[npairs + 1] receives where
- * each pair's bytes start in the buffer dcpgpu_match_fetch fills.  Any output may be NULL. */
+ * each pair's bytes start in the buffer dcpgpu_match_fetch fills.  Any output may be NULL; with
+ * text_off == NULL only the extents are computed (no decode tables needed, nothing to fetch). */
 int dcpgpu_match_build(dcpgpu_ctx *ctx, float epsilon, int is_rna, int32_t *hit, int32_t *hit_start,
                        int32_t *hit_stop, int64_t *text_off);
 int dcpgpu_match_fetch(dcpgpu_ctx *ctx, char *text);

@@ -14,7 +14,7 @@
  *     ignored (every profile is resident in HBM).  Rows come out in the reference's order
  *     whatever the number of shards.  The callback fires on shard 0 after every chunk of profiles
  *     (the reference: on partition 0 after every window); dcp_scan_interrupt is honoured between
- *     chunks ($DCP_CHUNK_CELLS DP cells each, default 4e10, about 0.1 s of GPU time).
+ *     chunks ($DCP_CHUNK_CELLS DP cells each, default 2e11, about 0.4 s of GPU time).
  *   * HMMER daemon (c-core/hmmer.c, thread.c:185-203): the third-party client libraries are
  *     not part of this build.  `port <= 0` runs WITHOUT the HMMER confirmation stage: every
  *     window with lrt >= 0 and a B..E segment yields a row, `evalue` is written as 0 and no
@@ -66,6 +66,10 @@ char const *dcp_error_string(int error_code);
 int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size, float *epsilon);
 /* Extension: GPUs (= profile shards) a set-up scan runs on. */
 int dcpb200_scan_num_gpus(struct dcp_scan const *);
+/* Extension: cumulative counters summed over the shards' GPU contexts (dcpgpu_counter): 0 = bytes
+ * copied host -> device, 1 = bytes copied device -> host, 2 = kernels launched, 3 = DP cells scored;
+ * and of the scan itself: 4 = windows scored, 5 = windows with lrt >= 0 (thread.c:119-121). */
+double dcpb200_scan_counter(struct dcp_scan const *, int what);
 
 /* Error codes 1..80 are the reference's (c-core/deciphon.h:34-116); only the ones this
  * library can return are named here.  81.. are new. */

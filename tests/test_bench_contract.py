@@ -31,6 +31,10 @@ def test_bench_never_routes_the_product_through_the_oracle():
     uses = [i for i, ln in enumerate(src.splitlines(), 1) if "oracle" in ln and "import" in ln]
     body = src.splitlines()
     for i in uses:
-        # every import of the oracle sits inside cpu_scan_sample (shared by both CPU legs)
+        # every import of the oracle sits inside the CPU legs: cpu_scan_sample (shared by cpu_baseline and
+        # --impl reference) and cpu_small_configs (the CPU side + parity check of configs 2 and 5)
         back = [ln for ln in body[:i] if ln.startswith("def ")]
-        assert back and back[-1].startswith("def cpu_scan_sample"), (i, body[i - 1])
+        assert back and back[-1].startswith(("def cpu_scan_sample", "def cpu_small_configs")), (i, body[i - 1])
+    # and the measured legs never call those functions
+    b200 = src[src.index("def run_b200"):src.index("def _measured_peaks")]
+    assert "cpu_scan_sample" not in b200 and "cpu_small_configs" not in b200 and "oracle" not in b200
