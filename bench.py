@@ -370,12 +370,12 @@ def plugin_leg(args, world, sizes, pool, nodes_of, reads, R, nsteps_total):
         d = {k: c1[k] - c0[k] for k in c0}
         with open(os.path.join(out, "products.tsv"), "rb") as fh:
             tsv = fh.read()
-        gpus = scan.num_gpus
+        gpus, shards = scan.num_gpus, scan.num_shards
         scan.free()
         return {"value": d["cells"] / secs / 1e9, "unit": "GCUPS", "seconds": secs, "cells": d["cells"],
                 "h2d_bytes_per_step": int(d["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(d["d2h_bytes"] / args.steps),
                 "launches": int(d["launches"]), "windows": int(d["windows"]), "lrt_windows": int(d["lrt_windows"]),
-                "reads_per_s": args.steps * R / secs, "gpus": gpus, "profiles": nprof,
+                "reads_per_s": args.steps * R / secs, "gpus": gpus, "shards": shards, "profiles": nprof,
                 "dcp_bytes": info["bytes"], "dcp_write_s": write_s, "setup_s": setup_s,
                 "rows_last_step": tsv.count(b"\n") - 1, "tsv_bytes_last_step": len(tsv),
                 "api": "dcp_batch_add x reads + dcp_scan_run -> products.tsv (libdeciphon_b200.so), num_threads = %d" % world,

@@ -10,14 +10,9 @@ static cudaError_t reg_t(ScoreArgs const &a, int sm_count, cudaStream_t st)
 {
   constexpr int T = ScoreCfg<W>::THREADS, G = ScoreCfg<W>::GROUPS;
   constexpr size_t SMEM = score_smem_bytes<Q, W>();
-  static bool configured = false;
-  cudaError_t e;
-  if (!configured)
-  {
-    e = cudaFuncSetAttribute(score_reg_kernel<Q, W, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  // per device and cheap: set on every launch (one process drives several GPUs, one context each)
+  cudaError_t e = cudaFuncSetAttribute(score_reg_kernel<Q, W, DUMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  if (e != cudaSuccess) return e;
   int per_sm = 0;
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_reg_kernel<Q, W, DUMP>, T, SMEM);
   if (e != cudaSuccess) return e;

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cerrno>
 #include <cmath>
 #include <cstdint>
@@ -77,6 +78,7 @@ struct Shard
   dcpgpu_ctx *gpu = nullptr;
   int device = 0;
   int p0 = 0, p1 = 0;
+  bool stagger = false; // not the first shard of its GPU
 };
 
 struct dcp_scan
@@ -92,7 +94,7 @@ struct dcp_scan
   std::atomic<bool> interrupted{false};
   std::atomic<int> done_proteins{0};
   std::atomic<long> windows{0}, lrt_windows{0}; // cumulative: windows scored / with lrt >= 0 (dcpb200_scan_counter)
-  double chunk_cells = 2e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
+  double chunk_cells = 1e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
 };
 
 namespace {
@@ -156,6 +158,19 @@ int mkdir_p(std::string const &dir)
   if (mkdir(dir.c_str(), 0755) == 0 || errno == EEXIST) return 0;
   return DCP_EMKDIR;
 }
+
+// DCP_TIMING=1: per-phase wall seconds of a dcp_scan_run on stderr (development aid)
+struct PhaseTimer
+{
+  double t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point mark = std::chrono::steady_clock::now();
+  void lap(int i)
+  {
+    auto const now = std::chrono::steady_clock::now();
+    t[i] += std::chrono::duration<double>(now - mark).count();
+    mark = now;
+  }
+};
 
 struct Row
 {
@@ -464,11 +479,15 @@ int dcp_scan_setup(struct dcp_scan *x, char const *dbfile, int port, int num_thr
   if (char const *env = getenv("DCP_CHUNK_CELLS"))
     if (atof(env) > 0) x->chunk_cells = atof(env);
 
-  // partitions -> GPUs: min(num_threads, visible devices, DCP_GPU_COUNT), starting at DCP_GPU_DEVICE
-  int first_device = 0, max_gpus = std::max(1, num_threads);
+  // partitions -> GPUs: min(num_threads, visible devices, DCP_GPU_COUNT), starting at DCP_GPU_DEVICE;
+  // every GPU takes DCP_SHARDS_PER_GPU (default 2) shards when the database is large enough: while
+  // one shard's host thread decodes hits and formats rows, the other shard's kernels keep the GPU busy
+  int first_device = 0, max_gpus = std::max(1, num_threads), shards_per_gpu = 2;
   if (char const *env = getenv("DCP_GPU_DEVICE")) first_device = atoi(env);
   if (char const *env = getenv("DCP_GPU_COUNT"))
     if (atoi(env) > 0) max_gpus = std::min(max_gpus, atoi(env));
+  if (char const *env = getenv("DCP_SHARDS_PER_GPU"))
+    if (atoi(env) > 0) shards_per_gpu = std::min(atoi(env), 8);
   // (the devices are looked at only once the file has proved to be a database: the reference's
   // error order, scan.c:102-108)
   auto world_max = [&](int *out) -> int {
@@ -489,12 +508,15 @@ int dcp_scan_setup(struct dcp_scan *x, char const *dbfile, int port, int num_thr
       x->abc_name = h.is_rna ? "rna" : "dna";
       int wm = 1;
       if (int const e = world_max(&wm)) return e;
-      int const world = std::max(1, std::min<int>(wm, (int)h.num_proteins)); // scan.c:105
+      int const gpus = std::max(1, std::min<int>(wm, (int)h.num_proteins)); // scan.c:105
+      int const spg = (long)h.num_proteins >= 128L * gpus * shards_per_gpu ? shards_per_gpu : 1;
+      int const world = gpus * spg;
       cuts = shard_cuts(h.protein_sizes, world);
       for (int r = 0; r < world; ++r)
       {
         Shard sh;
-        sh.device = first_device + r;
+        sh.device = first_device + r / spg;
+        sh.stagger = (r % spg) != 0;
         sh.p0 = cuts[(size_t)r];
         sh.p1 = cuts[(size_t)r + 1];
         int const e = dcpgpu_open(&sh.gpu, sh.device);
@@ -559,7 +581,13 @@ int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size
   return 0;
 }
 
-int dcpb200_scan_num_gpus(struct dcp_scan const *x) { return x ? (int)x->shards.size() : 0; }
+int dcpb200_scan_num_gpus(struct dcp_scan const *x)
+{
+  if (!x || x->shards.empty()) return 0;
+  return x->shards.back().device - x->shards.front().device + 1;
+}
+
+int dcpb200_scan_num_shards(struct dcp_scan const *x) { return x ? (int)x->shards.size() : 0; }
 
 double dcpb200_scan_counter(struct dcp_scan const *x, int what)
 {
@@ -595,8 +623,11 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
   int const S = (int)batch->seqs.size();
   uint32_t const flags = (x->multi_hits ? DCPGPU_MULTI_HITS : 0u) | (x->hmmer3_compat ? DCPGPU_HMMER3_COMPAT : 0u);
   int rc;
+  PhaseTimer tm;
+  bool const timing = getenv("DCP_TIMING") != nullptr;
   if ((rc = dcpgpu_reads_set(gpu, S, symbols.data(), offsets.data()))) return map_gpu_error(rc);
   if (sh.p1 <= sh.p0 || S == 0) return 0;
+  tm.lap(0);
 
   // cells of the first windows of one profile against the whole batch
   auto profile_cells = [&](int p) {
@@ -623,7 +654,9 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
         ++i1;
       }
       size_t const n = i1 - i0;
+      tm.lap(7);
       if ((rc = dcpgpu_trace_pairs(gpu, (int64_t)n, &pairs[i0], flags, nullptr, nullptr))) return map_gpu_error(rc);
+      tm.lap(2);
       std::vector<int32_t> hit(n), hstart(n), hstop(n);
       std::vector<int64_t> toff(n + 1, 0);
       rc = dcpgpu_match_build(gpu, x->epsilon, x->is_rna ? 1 : 0, hit.data(), hstart.data(), hstop.data(), toff.data());
@@ -631,6 +664,7 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
       if (rc) return map_gpu_error(rc);
       std::vector<char> text((size_t)toff[n] + 1);
       if ((rc = dcpgpu_match_fetch(gpu, text.data()))) return map_gpu_error(rc);
+      tm.lap(3);
       for (size_t i = 0; i < n; ++i)
       {
         if (!hit[i]) continue; // no B..E segment: thread.c:136,148
@@ -650,6 +684,7 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
         row.push_back('\n');
         rows->push_back(Row{gp, pr.seq, win_idx[i0 + i], std::move(row)});
       }
+      tm.lap(4);
       i0 = i1;
     }
     return 0;
@@ -659,19 +694,24 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
   while (c0 < sh.p1 && !x->interrupted)
   {
     // ---- the chunk [c0, c1): about chunk_cells DP cells of first windows ----
+    // (the second shard of a GPU starts with half a chunk: its host phases then fall into the
+    // other shard's score passes instead of coinciding with them)
+    double const target = (c0 == sh.p0 && sh.stagger) ? x->chunk_cells / 2 : x->chunk_cells;
     int c1 = c0;
     double cells = 0;
     do
     {
       cells += profile_cells(c1);
       ++c1;
-    } while (c1 < sh.p1 && cells < x->chunk_cells);
+    } while (c1 < sh.p1 && cells < target);
     int const P = c1 - c0, l0 = c0 - sh.p0; // shard-local profile indices l0 .. l0 + P
 
     // wave 0: the first window of every (sequence, profile), generated on the device
+    tm.lap(7);
     if ((rc = dcpgpu_score_grid(gpu, l0, l0 + P, 0, S, flags))) return map_gpu_error(rc);
     int64_t nhits = 0;
     if ((rc = dcpgpu_hits_fetch(gpu, 0, nullptr, &nhits))) return map_gpu_error(rc);
+    tm.lap(1);
     std::vector<int64_t> hit((size_t)nhits);
     if (nhits && (rc = dcpgpu_hits_fetch(gpu, nhits, hit.data(), &nhits))) return map_gpu_error(rc);
     x->windows += (long)P * S;
@@ -712,6 +752,7 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
       auto it = by_pair.find({p, s});
       if (it != by_pair.end()) owner[(size_t)i] = it->second;
     }
+    tm.lap(5);
     if ((rc = process_hits(hp, widx, hn, ha, owner))) return rc;
 
     // waves 1..: explicit windows of the pairs that are still active
@@ -730,8 +771,10 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
       }
       if (wp.empty()) break;
       std::vector<float> nulc(wp.size()), altc(wp.size());
+      tm.lap(7);
       if ((rc = dcpgpu_score_pairs(gpu, (int64_t)wp.size(), wp.data(), flags, nulc.data(), altc.data())))
         return map_gpu_error(rc);
+      tm.lap(6);
       std::vector<dcpgpu_pair> hp2;
       std::vector<int> widx2;
       std::vector<float> hn2, ha2;
@@ -757,6 +800,12 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
     if (shard_index == 0 && x->callback) x->callback(x->userdata); // rank 0 only, scan.c:196-198
     c0 = c1;
   }
+  tm.lap(7);
+  if (timing)
+    fprintf(stderr,
+            "[dcp_scan_run shard %zu] reads_set %.3f  grid+hit count %.3f  trace %.3f  match build+fetch %.3f  rows %.3f  "
+            "scores fetch + hit lists %.3f  later-window score passes %.3f  other host %.3f s\n",
+            shard_index, tm.t[0], tm.t[1], tm.t[2], tm.t[3], tm.t[4], tm.t[5], tm.t[6], tm.t[7]);
   return 0;
 }
 

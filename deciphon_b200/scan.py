@@ -39,6 +39,7 @@ SYMBOLS = [
     ("dcp_error_string", C.c_char_p, [C.c_int]),
     ("dcpb200_db_info", C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_long), C.POINTER(C.c_float)]),
     ("dcpb200_scan_num_gpus", C.c_int, [C.c_void_p]),
+    ("dcpb200_scan_num_shards", C.c_int, [C.c_void_p]),
     ("dcpb200_scan_counter", C.c_double, [C.c_void_p, C.c_int]),
 ]
 
@@ -135,8 +136,13 @@ class Scan:
 
     @property
     def num_gpus(self) -> int:
-        """GPUs (= profile shards) this scan runs on."""
+        """GPUs this scan runs on."""
         return lib.dcpb200_scan_num_gpus(self._cscan)
+
+    @property
+    def num_shards(self) -> int:
+        """Profile shards (one host thread each; DCP_SHARDS_PER_GPU per GPU for large databases)."""
+        return lib.dcpb200_scan_num_shards(self._cscan)
 
     def counters(self) -> dict:
         """Cumulative H2D / D2H bytes, kernel launches and DP cells of this scan's GPU contexts, windows

@@ -8,13 +8,15 @@
  * include/dcpgpu.h.  What differs from the reference, by design:
  *
  *   * dcp_scan_setup: the reference cuts the database into `num_threads` partitions, one per
- *     OpenMP thread (c-core/scan.c:95-152); here a partition is a GPU: min(num_threads, visible
- *     CUDA devices, $DCP_GPU_COUNT) shards of contiguous profiles balanced by core size, starting
- *     at device $DCP_GPU_DEVICE (default 0), one host thread each.  `cache` is accepted and
+ *     OpenMP thread (c-core/scan.c:95-152); here the partitions live on GPUs: min(num_threads,
+ *     visible CUDA devices, $DCP_GPU_COUNT) devices starting at $DCP_GPU_DEVICE (default 0), each
+ *     holding $DCP_SHARDS_PER_GPU (default 2; 1 for databases of fewer than 128 profiles per shard)
+ *     shards of contiguous profiles balanced by core size, one host thread per shard -- one
+ *     shard's kernels fill the GPU while the other's host thread decodes hits and formats rows.  `cache` is accepted and
  *     ignored (every profile is resident in HBM).  Rows come out in the reference's order
  *     whatever the number of shards.  The callback fires on shard 0 after every chunk of profiles
  *     (the reference: on partition 0 after every window); dcp_scan_interrupt is honoured between
- *     chunks ($DCP_CHUNK_CELLS DP cells each, default 2e11, about 0.4 s of GPU time).
+ *     chunks ($DCP_CHUNK_CELLS DP cells each, default 1e11, about 0.2 s of GPU time).
  *   * HMMER daemon (c-core/hmmer.c, thread.c:185-203): the third-party client libraries are
  *     not part of this build.  `port <= 0` runs WITHOUT the HMMER confirmation stage: every
  *     window with lrt >= 0 and a B..E segment yields a row, `evalue` is written as 0 and no
@@ -64,8 +66,9 @@ char const *dcp_error_string(int error_code);
 /* Extension: parse a .dcp database (either float encoding) without touching
  * the GPU; reports the number of profiles, the total core size and epsilon. */
 int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size, float *epsilon);
-/* Extension: GPUs (= profile shards) a set-up scan runs on. */
+/* Extension: GPUs a set-up scan runs on, and the profile shards (host threads) it is cut into. */
 int dcpb200_scan_num_gpus(struct dcp_scan const *);
+int dcpb200_scan_num_shards(struct dcp_scan const *);
 /* Extension: cumulative counters summed over the shards' GPU contexts (dcpgpu_counter): 0 = bytes
  * copied host -> device, 1 = bytes copied device -> host, 2 = kernels launched, 3 = DP cells scored;
  * and of the scan itself: 4 = windows scored, 5 = windows with lrt >= 0 (thread.c:119-121). */

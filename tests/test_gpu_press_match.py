@@ -220,3 +220,52 @@ def test_snap_archive_layout(tmp_path, golden_profiles, golden_reads):
     dcs = make_snap_archive(str(tmp_path / "snap"), str(tmp_path / "snap.dcs"))
     names = zipfile.ZipFile(dcs).namelist()
     assert "snap/products.tsv" in names and "snap/hmmer/" in names and not (tmp_path / "snap").exists()
+
+
+def test_window_waves_over_the_c_abi_match_dcp_scan_run(tmp_path, node_pool):
+    """deciphon_b200.waves (bench.py's measured leg: window.c waves driven over the C ABI) and
+    dcp_scan_run (the C++ host loop) score exactly the same windows: same DP cells, same number of
+    windows through the lrt gate -- every later window's start depends on the hits decoded before it."""
+    from deciphon_b200 import synth, waves
+    from deciphon_b200.device import PAIR_DTYPE, Device
+    from deciphon_b200.scan import Batch, Scan, Sequence
+    rng = np.random.default_rng(5)
+    sizes = np.asarray([20, 24, 31, 39, 40, 64, 300], dtype=np.int64)
+    nodes = [synth.synth_profile_nodes(np.random.default_rng([5, 1, p]), int(sizes[p]), node_pool) for p in range(len(sizes))]
+    reads = []
+    for i in range(12):
+        x = synth.random_read(rng, 2000)
+        if i % 3 == 0:  # embed the consensus of a small profile a few times so that later windows hold hits
+            q = int(rng.integers(0, 4))
+            cons = synth.consensus_dna(node_pool, nodes[q][0])
+            parts = []
+            for _ in range(6):
+                parts += [synth.random_read(rng, int(rng.integers(100, 300))), cons]
+            x = synth.fixed_length(rng, np.concatenate(parts), 2000)
+        reads.append(synth.mutate(rng, x, 0.05)[:1900 + 10 * i])
+    db = str(tmp_path / "w.dcp")
+    synth.write_synth_dcp(db, sizes, node_pool, lambda p: nodes[p])
+    batch = Batch()
+    for i, r in enumerate(reads):
+        batch.add(Sequence(i, f"r{i}", "".join("ACGT"[v] for v in r)))
+    with Scan(db, 0, 1, True, False, False) as scan:
+        scan.run(str(tmp_path / "o"), batch)
+        want = scan.counters()
+    with Device(0) as dev:
+        first = dev.pool_add(node_pool.emission, node_pool.trans)
+        for p in range(len(sizes)):
+            dev.profile_add(int(sizes[p]), nodes[p][1], node_pool.null_emission, node_pool.bg_emission, nodes[p][0] + first)
+        dev.set_reads(reads)
+        lens = np.asarray([len(r) for r in reads], dtype=np.int64)
+        R = len(reads)
+        dev.score_grid(0, len(sizes), 0, R, True, False)
+        idx = dev.hits_fetch()
+        pr = np.zeros(len(idx), dtype=PAIR_DTYPE)
+        pr["profile"], pr["seq"] = idx // R, idx % R
+        pr["len"] = waves.first_windows(sizes, lens)[idx // R, idx % R]
+        hit, _hs, he, _n = waves.trace_hits(dev, pr, True, False, Ks=sizes)
+        w = waves.later_waves(dev, sizes, 0, lens, pr, hit, he, True, False)
+        got = dev.counters()
+    assert w["pairs"] > 0 and w["hits"] > 0  # later windows exist and some hold hits
+    assert got["cells"] == want["cells"]
+    assert len(idx) + w["hits"] == want["lrt_windows"] and len(sizes) * R + w["pairs"] == want["windows"]
