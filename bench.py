@@ -76,6 +76,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=20261018)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work of the cpu_baseline leg (and cap of a reference-arm step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--contexts", type=int, default=2, help="C ABI contexts (sub-shards, host threads) per GPU in the measured legs")
     ap.add_argument("--no-plugin", action="store_true", help="skip the dcp_scan_run legs (e2e falls back to the C ABI leg)")
     ap.add_argument("--plugin-profiles", type=int, default=0,
                     help="profiles of the database the dcp_scan_run leg scans (0 = all; fewer if the disk has no room)")
@@ -295,7 +296,7 @@ def workload_config(args, sizes, shard):
         "profiles": args.profiles, "reads_per_step": args.reads_per_step * args.gpus,
         "reads_per_step_per_gpu": args.reads_per_step, "read_len": args.read_len,
         "multi_hits": True, "hmmer3_compat": False, "seed": args.seed,
-        "parallelism": f"profile-sharded x{args.gpus}, no collective",
+        "parallelism": f"profile-sharded x{args.gpus}, no collective; {args.contexts} contexts (sub-shards, host threads) per GPU",
         "l2_policy": "inputs larger than L2 (profile tables >> 126 MB); no flush",
         "shard": shard,
     }
@@ -490,78 +491,123 @@ def run_b200(args, rank, local_rank, world):
             nodes[p] = profile_nodes(args.seed, p, sizes[p], pool)
         return nodes[p]
 
-    dev = Device(local_rank)
+    # args.contexts C-ABI contexts per GPU, each holding a contiguous sub-shard (balanced by core size) on
+    # its own stream and driven by its own host thread: while one context's thread collects hits,
+    # traces them and prepares the next windows, the other context's score kernels keep the GPU busy
     stream = torch.cuda.current_stream()
-    dev.set_stream(stream.cuda_stream)
+    nctx = max(1, min(args.contexts, (p1 - p0) // 64 or 1))
+    sub = [p0 + int(c) for c in shard_bounds(sizes[p0:p1], nctx)]
+    devs, streams = [], []
     t_build = time.time()
-    first = dev.pool_add(pool.emission, pool.trans)
-    for p in range(p0, p1):
-        ids, bmk = nodes_of(p)
-        dev.profile_add(int(sizes[p]), bmk, pool.null_emission, pool.bg_emission, ids + first)
-    dev.sync()
+    for c in range(nctx):
+        dev = Device(local_rank)
+        st_c = torch.cuda.Stream()
+        dev.set_stream(st_c.cuda_stream)
+        first = dev.pool_add(pool.emission, pool.trans)
+        for p in range(sub[c], sub[c + 1]):
+            ids, bmk = nodes_of(p)
+            dev.profile_add(int(sizes[p]), bmk, pool.null_emission, pool.bg_emission, ids + first)
+        dev.sync()
+        devs.append(dev)
+        streams.append(st_c)
     t_build = time.time() - t_build
-    nprof = p1 - p0
-    Ks = sizes[p0:p1]
     L = args.read_len
     nsteps_total = args.warmup + args.steps
-    multi_window = int(np.count_nonzero(np.minimum(Ks * 50, 100000) < L))
+    Ks_all = sizes[p0:p1]
+    multi_window = int(np.count_nonzero(np.minimum(Ks_all * 50, 100000) < L))
 
-    def run_legs(R, reads, host_buffers):
-        """args.warmup + args.steps steps of R reads each.  host_buffers: the step's reads are
-        handed over as host symbols (packed + copied inside the step) and every score comes back."""
-        win = np.minimum(np.minimum(Ks * 50, 100000), L).astype(np.int32)  # first window per profile
+    def run_legs(R, reads, host_buffers, kernels_only=False):
+        """args.warmup + args.steps steps of R reads each.  host_buffers: the step's reads are handed over
+        as host symbols (packed + copied inside the step) and every score comes back.  kernels_only:
+        just the score pass of the first windows, one context at a time (the roofline's kernel time)."""
         lens = np.full(R, L, dtype=np.int64)
         offs = np.arange(R + 1, dtype=np.int64) * L
         pinned = None
         if host_buffers:
             pinned = [torch.from_numpy(np.concatenate(reads[i * R:(i + 1) * R])).pin_memory() for i in range(nsteps_total)]
         else:
-            dev.set_reads(reads)
+            for dev in devs:
+                dev.set_reads(reads)
 
-        def step(i, st):
+        def step(c, i, st):
+            dev, Ks = devs[c], sizes[sub[c]:sub[c + 1]]
+            nprof = len(Ks)
+            win = np.minimum(np.minimum(Ks * 50, 100000), L).astype(np.int32)  # first window per profile
             seq0 = 0 if host_buffers else i * R
             if host_buffers:
                 dev.set_reads_packed(pinned[i].numpy(), offs)
             dev.score_grid(0, nprof, seq0, seq0 + R, True, False)
+            if kernels_only:
+                st["score_ms"] += dev.last_kernel_ms()
+                st["grid_cells"] += dev.last_cells()
+                return
             if host_buffers:
                 dev.scores_fetch(nprof * R)
             idx = dev.hits_fetch()
             pr = np.zeros(len(idx), dtype=PAIR_DTYPE)
             pr["profile"], pr["seq"], pr["start"], pr["len"] = idx // R, seq0 + idx % R, 0, win[idx // R]
-            st["score_ms"] += dev.last_kernel_ms()
-            st["grid_cells"] += dev.last_cells()
             hit, _hs, he, nst = waves.trace_hits(dev, pr, True, False, Ks=Ks)
             st["steps"] += nst
             st["hits"] += len(pr)
-            if multi_window:  # windows 2.. of the profiles of fewer than L/50 nodes (window.c:13-37)
+            if np.any(np.minimum(Ks * 50, 100000) < L):  # windows 2.. of the profiles of fewer than L/50 nodes
                 w = waves.later_waves(dev, Ks, seq0, lens, pr, hit, he, True, False)
                 st["hits"] += w["hits"]
                 st["steps"] += w["steps"]
                 st["later_windows"] += w["pairs"]
 
         zero = lambda: {"score_ms": 0.0, "grid_cells": 0.0, "hits": 0, "steps": 0, "later_windows": 0}  # noqa: E731
-        st = zero()
-        for i in range(args.warmup):
-            step(i, st)
-        st = zero()
+
+        def run_steps(first_step, last_step):
+            """Every context runs its steps on its own thread (free-running: their phases interleave)."""
+            stats = [zero() for _ in range(nctx)]
+            errs = []
+
+            def work(c):
+                try:
+                    torch.cuda.set_device(local_rank)
+                    for i in range(first_step, last_step):
+                        step(c, i, stats[c])
+                except BaseException as e:  # noqa: BLE001
+                    errs.append(e)
+
+            if kernels_only or nctx == 1:
+                for c in range(nctx):
+                    work(c)
+            else:
+                ts = [threading.Thread(target=work, args=(c,)) for c in range(nctx)]
+                for t in ts:
+                    t.start()
+                for t in ts:
+                    t.join()
+            if errs:
+                raise errs[0]
+            return {k: sum(s_[k] for s_ in stats) for k in stats[0]}
+
+        if not kernels_only:  # (the kernel-only leg follows the timed steps: already warm)
+            run_steps(0, args.warmup)
         sampler = ClockSampler(local_rank)
         sampler.start()
-        c0 = dev.counters()
+        c0 = [dev.counters() for dev in devs]
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        for i in range(args.warmup, nsteps_total):
-            step(i, st)
+        for s_ in streams:
+            s_.wait_event(e0)
+        st = run_steps(args.warmup, nsteps_total)
+        for s_ in streams:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            stream.wait_event(ev)
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0
-        c1 = dev.counters()
+        c1 = [dev.counters() for dev in devs]
         st["ms"] = max_over_ranks(e0.elapsed_time(e1))
         st["wall_s"] = max_over_ranks(wall)
         st["clocks"] = sampler.summary()
-        for k in c0:
-            st[k] = c1[k] - c0[k]
+        for k in c0[0]:
+            st[k] = sum(b_[k] - a_[k] for a_, b_ in zip(c0, c1))
         st["total_cells"] = sum_over_ranks(st["cells"])
         st["total_hits"] = sum_over_ranks(float(st["hits"]))
         return st
@@ -570,6 +616,8 @@ def run_b200(args, rank, local_rank, world):
     R = args.reads_per_step * world
     reads = make_reads(args.seed, 0, nsteps_total * R, L, sizes, pool)
     v = run_legs(R, reads, host_buffers=False)
+    # ---- phase 1b: the score kernels alone, one context at a time (roofline: no concurrent work in their time) ----
+    kern = run_legs(R, reads, host_buffers=False, kernels_only=True)
     # ---- phase 2: the same steps through the C ABI with host buffers ("e2e_cabi") ----
     c = run_legs(R, reads, host_buffers=True)
     # ---- phase 3 (N > 1): strong scaling, a fixed batch of 96 reads over the N shards ----
@@ -583,13 +631,14 @@ def run_b200(args, rank, local_rank, world):
     if rank == 0:
         for name, mode in (("fadd_vimnmx3_2to1", 6), ("fadd_fmnmx3_2to1", 5), ("fadd_fmnmx_1to1", 0), ("fadd", 1)):
             try:
-                peaks[name] = dev.alu_peak(mode)
+                peaks[name] = devs[0].alu_peak(mode)
             except Exception:
                 peaks[name] = None
-    db_bytes = dev.profile_bytes
-    dev.close()
+    db_bytes = sum(dev.profile_bytes for dev in devs)
+    for dev in devs:
+        dev.close()
     torch.cuda.empty_cache()
-    score_ms_max = max_over_ranks(v["score_ms"])
+    score_ms_max = max_over_ranks(kern["score_ms"])
 
     # ---- phase 4: end to end through the reference API ("e2e"), one process driving all N GPUs ----
     plugin = None
@@ -616,7 +665,7 @@ def run_b200(args, rank, local_rank, world):
         # device time, against the issue ceiling (one lane-op per lane and clock at the sampled SM clock)
         mhz = clocks.get("sm_mhz") or 1965.0
         nominal = 148 * 128 * mhz * 1e6 / 1e12
-        achieved = OPS_PER_CELL * v["grid_cells"] / (v["score_ms"] * 1e-3) / 1e12
+        achieved = OPS_PER_CELL * kern["grid_cells"] / (kern["score_ms"] * 1e-3) / 1e12
         traffic_bytes = measured_traffic() if (world == 1 and args.profiles == 20000 and args.reads_per_step == 96
                                                and args.read_len == 2000) else None
         mix = peaks.get("fadd_vimnmx3_2to1")
@@ -654,8 +703,10 @@ def run_b200(args, rank, local_rank, world):
                          "kernel": "score pass of the first windows = score_row_kernel<Q,SEG,MODE> (row_kernel.cuh): whole "
                                    "profiles of <= 256 nodes (SEG 32/16/8/4), 256-node segments + tail of larger ones "
                                    "(speculative B, exact redo by score_reg_kernel<Q,W>), generic_kernel<false> for the rest; rank 0",
-                         "ops_per_cell": OPS_PER_CELL, "kernel_gcups": v["grid_cells"] / (v["score_ms"] * 1e-3) / 1e9,
-                         "kernel_ms_per_step": v["score_ms"] / args.steps,
+                         "ops_per_cell": OPS_PER_CELL, "kernel_gcups": kern["grid_cells"] / (kern["score_ms"] * 1e-3) / 1e9,
+                         "kernel_ms_per_step": kern["score_ms"] / args.steps,
+                         "kernel_timing": "CUDA events around the score pass of each context run alone (phase 1b), the same "
+                                          "batches as the timed steps",
                          "hbm_gbs_measured": _measured_peaks().get("hbm_gbs")},
             "hits_per_step": v["hits"] / args.steps, "path_steps_per_step": v["steps"] / args.steps,
             "later_windows_per_step": v["later_windows"] / args.steps, "multi_window_profiles_rank0": multi_window,

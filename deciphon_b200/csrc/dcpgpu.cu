@@ -16,6 +16,7 @@
 #include "trace_walk.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -131,7 +132,10 @@ struct dcpgpu_ctx
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // side streams: the per-class kernels of one pass are independent, so they are spread over these
   // and the tail of one class overlaps the head of the next
-  static constexpr int NSIDE = 4;
+#ifndef DCPGPU_NSIDE
+#define DCPGPU_NSIDE 8
+#endif
+  static constexpr int NSIDE = DCPGPU_NSIDE;
   cudaStream_t side[NSIDE] = {};
   cudaEvent_t ev_fork = nullptr, ev_join[NSIDE] = {};
   bool forked = false;
@@ -200,6 +204,22 @@ int fail_cuda(dcpgpu_ctx *c, cudaError_t e, char const *what)
   if (c) c->err = buf;
   return e == cudaErrorMemoryAllocation ? DCPGPU_ENOMEM : DCPGPU_ECUDA;
 }
+
+// DCPGPU_TIMING=1: host wall time of the phases of a trace pass on stderr (development aid)
+struct TracePhases
+{
+  bool on = std::getenv("DCPGPU_TIMING") != nullptr;
+  double t[6] = {0, 0, 0, 0, 0, 0};
+  std::chrono::steady_clock::time_point mark = std::chrono::steady_clock::now();
+  void lap(int i, cudaStream_t st)
+  {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto const now = std::chrono::steady_clock::now();
+    t[i] += std::chrono::duration<double>(now - mark).count();
+    mark = now;
+  }
+};
 
 int fail(dcpgpu_ctx *c, int code, char const *what)
 {
@@ -1616,6 +1636,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
 {
   if (!ctx || npairs < 0 || (npairs && !pairs)) return fail(ctx, DCPGPU_EINVAL, "trace_pairs: bad argument");
   CU(cudaSetDevice(ctx->device));
+  TracePhases ph;
   int rc, maxlen = 1;
   ctx->traced = false;
   ctx->matched = false;
@@ -1665,6 +1686,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(counted_copy(ctx, ctx->d_xnode_off, ctx->t_xnode_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(counted_copy(ctx, ctx->d_node_off, ctx->t_node_off.data(), (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemsetAsync(ctx->d_counters + SLOT_TRACE_CUR, 0, 5 * sizeof(unsigned long long), ctx->stream));
+  ph.lap(0, ctx->stream);
 
   // ---- fast route: pairs whose profile runs on a register kernel -------------------------------
   // value dump by score_reg_kernel<Q,W,DUMP> + parallel argmin kernel (trace_argmin.cuh), in chunks
@@ -1674,35 +1696,41 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     (kernel_class(ctx, pairs[i].profile) != 0 ? fast : slow).push_back(i);
   if (!fast.empty())
   {
-    size_t fr = 0, tot = 0;
-    CU(cudaMemGetInfo(&fr, &tot));
-    size_t const have = ctx->dump_cap * sizeof(float);
-    size_t const budget = std::min<size_t>((fr + have) / 2, size_t(24) << 30) / sizeof(float);
     if ((rc = ensure(ctx, ctx->d_dump_off, ctx->dump_off_cap, n))) return rc;
     // class-major: every launch then holds many pairs of ONE kernel class
     std::vector<std::vector<long long>> by_class(NCLASS);
     for (long long i : fast) by_class[(size_t)kernel_class(ctx, pairs[i].profile)].push_back(i);
-    // size the dump buffer ONCE (a full round, or the largest single pair): reallocating tens of
-    // GB between launches costs more than the kernels
+    // Size the dump buffer ONCE (a full round, or the largest single pair): reallocating tens of GB
+    // between launches costs more than the kernels.  The device is asked for its free memory only
+    // when the buffer has to grow (the query itself costs tens of ms on a busy context).
+    size_t budget = ctx->dump_cap; // floats a round may use
     {
-      size_t need = 0, all = 0;
+      size_t single = 0, all = 0;
       for (long long i : fast)
       {
         size_t const f = DumpView::floats(pairs[i].len, ctx->h_profiles[(size_t)pairs[i].profile].Kpad);
-        need = std::max(need, f);
+        single = std::max(single, f);
         all += f;
       }
-      need = std::max(need, std::min(all, budget));
-      // a trace that large is a burst of hits and bursts come in all sizes: take the whole budget
-      // once instead of growing (and re-allocating tens of GB) burst after burst
-      if (need > ctx->dump_cap && need > (size_t(1) << 28)) need = std::max(need, budget);
-      if (need > ctx->dump_cap)
+      if (all > ctx->dump_cap)
       {
-        if (ctx->d_dump) CU(cudaFree(ctx->d_dump));
-        ctx->d_dump = nullptr;
-        ctx->dump_cap = 0;
-        CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_dump), need * sizeof(float)));
-        ctx->dump_cap = need;
+        size_t fr = 0, tot = 0;
+        CU(cudaMemGetInfo(&fr, &tot));
+        size_t const have = ctx->dump_cap * sizeof(float);
+        size_t const room = std::min<size_t>((fr + have) / 2, size_t(24) << 30) / sizeof(float);
+        size_t need = std::max(single, std::min(all, room));
+        // a trace that large is a burst of hits and bursts come in all sizes: take the whole budget
+        // once instead of growing (and re-allocating tens of GB) burst after burst
+        if (need > (size_t(1) << 28)) need = std::max(need, room);
+        if (need > ctx->dump_cap)
+        {
+          if (ctx->d_dump) CU(cudaFree(ctx->d_dump));
+          ctx->d_dump = nullptr;
+          ctx->dump_cap = 0;
+          CU(cudaMalloc(reinterpret_cast<void **>(&ctx->d_dump), need * sizeof(float)));
+          ctx->dump_cap = need;
+        }
+        budget = ctx->dump_cap;
       }
     }
     // Rounds bounded by the dump budget; inside a round every kernel class present gets its own
@@ -1833,7 +1861,9 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
       }
       return 0;
     };
+    ph.lap(1, ctx->stream);
     if ((rc = run_fast())) return rc;
+    ph.lap(2, ctx->stream);
     if (!keep)
     { // a path that outgrew its slot was only counted: give every pair its exact size and redo
       unsigned long long over = 0;
@@ -1858,6 +1888,7 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     }
   }
 
+  ph.lap(3, ctx->stream);
   // ---- slow route (profiles the register kernels cannot run: K > 2048 or a negative cost) ----
   // Classes by profile size: one warp per pair up to K = 256 (throughput), a CTA of 2/4/8 warps
   // per pair above (the pass would otherwise last as long as its largest profile).
@@ -1928,10 +1959,15 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
     else { if ((rc = launch_trace_cta<8>(ctx, g, tmaxK[3], tgrid[3], scr))) return rc; }
   }
 
+  ph.lap(4, ctx->stream);
   std::vector<float2> h(n);
   CU(counted_copy(ctx, h.data(), ctx->d_tout, n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
   CU(counted_copy(ctx, ctx->t_nsteps.data(), ctx->d_nsteps, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  ph.lap(5, ctx->stream);
+  if (ph.on)
+    fprintf(stderr, "[trace_pairs %lld pairs] prep+H2D %.4f  dump sizing %.4f  dump+walk rounds %.4f  overflow redo %.4f  slow route %.4f  D2H %.4f s\n",
+            (long long)npairs, ph.t[0], ph.t[1], ph.t[2], ph.t[3], ph.t[4], ph.t[5]);
   for (size_t i = 0; i < n; ++i)
   {
     if (alt_cost) alt_cost[i] = h[i].y;

@@ -94,7 +94,7 @@ struct dcp_scan
   std::atomic<bool> interrupted{false};
   std::atomic<int> done_proteins{0};
   std::atomic<long> windows{0}, lrt_windows{0}; // cumulative: windows scored / with lrt >= 0 (dcpb200_scan_counter)
-  double chunk_cells = 1e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
+  double chunk_cells = 4e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
 };
 
 namespace {

@@ -16,7 +16,7 @@
  *     ignored (every profile is resident in HBM).  Rows come out in the reference's order
  *     whatever the number of shards.  The callback fires on shard 0 after every chunk of profiles
  *     (the reference: on partition 0 after every window); dcp_scan_interrupt is honoured between
- *     chunks ($DCP_CHUNK_CELLS DP cells each, default 1e11, about 0.2 s of GPU time).
+ *     chunks ($DCP_CHUNK_CELLS DP cells each, default 4e11, about 0.8 s of GPU time: every chunk boundary drains the GPU, about 30 ms).
  *   * HMMER daemon (c-core/hmmer.c, thread.c:185-203): the third-party client libraries are
  *     not part of this build.  `port <= 0` runs WITHOUT the HMMER confirmation stage: every
  *     window with lrt >= 0 and a B..E segment yields a row, `evalue` is written as 0 and no

@@ -23,6 +23,8 @@ def main():
     sizes = synth.core_sizes(np.random.default_rng(seed), 20000)[:nprof]
     nodes = [bench.profile_nodes(seed, p, sizes[p], pool) for p in range(nprof)]
     reads = bench.make_reads(seed, 0, 3 * R, L, synth.core_sizes(np.random.default_rng(seed), 20000), pool)
+    if os.environ.get("SKIP_CABI"):
+        return plugin(nprof, R, sizes, pool, nodes, reads)
     dev = Device(0)
     first = dev.pool_add(pool.emission, pool.trans)
     for p in range(nprof):
@@ -48,13 +50,22 @@ def main():
         print(f"step {i}: grid+hits {d[0]:.1f} ms (kernels {kms:.1f})  trace+fetch {d[1]:.1f}  extents {d[2]:.1f}  "
               f"later waves {d[3]:.1f} ({w})  hits {len(idx)} path steps {int(off[-1])}", flush=True)
     dev.close()
+    if not os.environ.get("SKIP_PLUGIN"):
+        plugin(nprof, R, sizes, pool, nodes, reads)
+
+
+def plugin(nprof, R, sizes, pool, nodes, reads):
     from deciphon_b200.scan import Batch, Scan, Sequence
     root = tempfile.mkdtemp(prefix="dcpprof_", dir="/tmp")
     db = os.path.join(root, "p.dcp")
     synth.write_synth_dcp(db, sizes, pool, lambda p: nodes[p])
     os.environ["DCP_TIMING"] = "1"
-    for spg in (1, 2, 3):
-        os.environ["DCP_SHARDS_PER_GPU"] = str(spg)
+    cfgs = sys.argv[3].split(",") if len(sys.argv) > 3 else ["1:1e11", "2:1e11", "3:1e11"]
+    for cfg in cfgs:
+        spg, chunk = cfg.split(":")
+        os.environ["DCP_SHARDS_PER_GPU"] = spg
+        os.environ["DCP_CHUNK_CELLS"] = chunk
+        print("== config", cfg, flush=True)
         with Scan(db, 0, 1, True, False, False) as scan:
             print(f"== {scan.num_shards} shard(s) on {scan.num_gpus} GPU", flush=True)
             for i in (0, 1, 0, 1):
