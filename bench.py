@@ -456,7 +456,7 @@ def run_b200(args, rank, local_rank, world):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (deciphon_b200 has no CPU fallback)")
     torch.cuda.set_device(local_rank)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line unless the caller asks for more
+    # (NCCL_DEBUG is left to the caller: unset, NCCL prints nothing and stdout is the one JSON line)
     cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
