@@ -841,6 +841,7 @@ int begin_pass(dcpgpu_ctx *ctx, size_t npairs)
   if ((rc = ensure(ctx, ctx->d_out, ctx->out_cap, npairs))) return rc;
   CU(cudaMemsetAsync(ctx->d_counters, 0, NSLOTS * sizeof(unsigned long long), ctx->stream));
   ctx->forked = false;
+  ctx->pinned = nullptr;
   ctx->last_cells = 0;
   ctx->last_redo = 0;
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
@@ -952,7 +953,7 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
   if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ctx->d_counters), NSLOTS * sizeof(unsigned long long));
   if (e != cudaSuccess)
   {
-    delete ctx;
+    dcpgpu_close(ctx); // destroys whatever was created (every handle starts out null)
     return DCPGPU_ECUDA;
   }
   *out = ctx;
@@ -1638,6 +1639,8 @@ int dcpgpu_trace_pairs(dcpgpu_ctx *ctx, int64_t npairs, dcpgpu_pair const *pairs
   CU(cudaSetDevice(ctx->device));
   TracePhases ph;
   int rc, maxlen = 1;
+  ctx->forked = false; // a failed pass may have left the side streams forked: never route to them unjoined
+  ctx->pinned = nullptr;
   ctx->traced = false;
   ctx->matched = false;
   ctx->steps_compact = false;
