@@ -144,24 +144,29 @@ class ClockSampler(threading.Thread):
 
 # ---- reference / CPU leg --------------------------------------------------------------------
 
-def balanced_sample(sizes, cores, per_thread, seed):
-    """K-stratified sample of per_thread x cores profiles, ordered so that the reference's
-    contiguous count partitions (scan.c:188-208, partition_size.c:13-16: cores partitions of
-    per_thread consecutive profiles) carry near-equal sum K -- what partitioning 20,000 profiles
-    by count gives the real scan (1,250 profiles per thread average out), and what a sample of
-    one or two profiles per thread does not."""
-    nprof = per_thread * cores
+def stratified_pick(sizes, nprof):
+    """nprof profiles at evenly spaced ranks of the core-size distribution, largest first."""
     order = np.argsort(sizes, kind="stable")
-    pick = order[np.linspace(0, len(order) - 1, nprof).round().astype(int)][::-1]  # largest first
+    return order[np.linspace(0, len(order) - 1, nprof).round().astype(int)][::-1]
+
+
+def deal_partitions(pick, cost, cores, per_thread, seed):
+    """Order the sample so that the reference's contiguous count partitions (scan.c:188-208,
+    partition_size.c:13-16: `cores` partitions of `per_thread` consecutive profiles) carry near-equal
+    cost -- what partitioning 20,000 profiles by count gives the real scan (1,250 profiles per thread
+    average out to a few per cent), and what a sample of one or two profiles per thread does not.
+    cost[i] = measured single-thread seconds of pick[i] (time is not linear in the core size: short
+    profiles pay a per-row overhead), dealt largest first in a snake."""
+    by_cost = np.argsort(-np.asarray(cost), kind="stable")
     parts = [[] for _ in range(cores)]
-    for r in range(per_thread):  # snake deal: round r hands one profile to every partition
-        row = pick[r * cores:(r + 1) * cores]
-        for j, p in enumerate(row if r % 2 == 0 else row[::-1]):
-            parts[j].append(int(p))
+    for r in range(per_thread):  # round r hands one profile to every partition
+        row = by_cost[r * cores:(r + 1) * cores]
+        for j, i in enumerate(row if r % 2 == 0 else row[::-1]):
+            parts[j].append(int(i))
     rng = np.random.default_rng(seed)
     for part in parts:
         rng.shuffle(part)  # mixed sizes inside a partition, like a real database
-    return np.asarray([p for part in parts for p in part], dtype=np.int64)
+    return np.asarray([i for part in parts for i in part], dtype=np.int64)
 
 
 def cpu_scan_sample(args, sizes, pool, target_seconds, simd=None):
@@ -178,7 +183,7 @@ def cpu_scan_sample(args, sizes, pool, target_seconds, simd=None):
         os.environ.pop("DCP_REF_SIMD", None)
     cores = os.cpu_count() or 1
     per_thread = 32
-    pick = balanced_sample(sizes, cores, per_thread, args.seed)
+    pick = stratified_pick(sizes, per_thread * cores)
     profs = []
     for p in pick:
         ids, bmk = profile_nodes(args.seed, int(p), sizes[p], pool)
@@ -187,6 +192,10 @@ def cpu_scan_sample(args, sizes, pool, target_seconds, simd=None):
                      np.concatenate([tr, tr[-1:]]), np.concatenate([em, em[-1:]]), bmk)
         profs.append(ref.profile(pr.costs()))
     probe_reads = make_reads(args.seed, 0, 2, args.read_len, sizes, pool)
+    # every profile's own single-thread cost on one read, then the balanced deal
+    cost = [min(ref.scan([pf], probe_reads[:1], True, False, 1)["seconds"] for _ in range(2)) for pf in profs]
+    deal = deal_partitions(pick, cost, cores, per_thread, args.seed)
+    pick, profs = pick[deal], [profs[i] for i in deal]
     ref.scan(profs, probe_reads, True, False, cores)  # first touch of the tables
     t = ref.scan(profs, probe_reads, True, False, cores)
     rate = t["cells"] / max(t["seconds"], 1e-9)
@@ -196,8 +205,8 @@ def cpu_scan_sample(args, sizes, pool, target_seconds, simd=None):
     r = ref.scan(profs, reads, True, False, cores)
     ts = r["thread_seconds"]
     gcups = r["cells"] / r["seconds"] / 1e9
-    sample = (f"{len(pick)} K-stratified profiles = {per_thread} per thread x {cores} threads, sum-K-balanced count "
-              f"partitions (sum K = {int(sizes[pick].sum())}) x {nreads} reads of {args.read_len} nt, every window.c "
+    sample = (f"{len(pick)} K-stratified profiles = {per_thread} per thread x {cores} threads, count partitions balanced by "
+              f"each profile's measured single-thread time (sum K = {int(sizes[pick].sum())}) x {nreads} reads of {args.read_len} nt, every window.c "
               f"window, xtrans + null + alt Viterbi per window, trellis+unzip for lrt>=0 ({r['hits']} hits), "
               f"{r['cells']:.3e} cells in {r['seconds']:.2f} s; per-thread busy {ts.min():.2f}..{ts.max():.2f} s, "
               f"parallel efficiency {r['parallel_efficiency']:.3f}, {gcups / cores:.4f} GCUPS per core; "
@@ -236,7 +245,10 @@ def cpu_baseline_record(args, sizes, pool, gpu_small=None):
     CPU side (and parity check) of the config 2 / config 5 legs."""
     c = cpu_scan_sample(args, sizes, pool, args.cpu_seconds)
     rec = {"value": c["gcups"], "unit": "GCUPS", "cores": c["cores"], "kind": "reference", "sample": c["sample"],
-           "parallel_efficiency": c["parallel_efficiency"]}
+           "parallel_efficiency": c["parallel_efficiency"],
+           # what the same threads would deliver with no idle time at all (sum of the threads' busy-time rates):
+           # an upper bound for the reference on this host, whatever the partitioning
+           "value_at_perfect_balance": c["gcups"] / max(c["parallel_efficiency"], 1e-9)}
     wide = os.path.basename(c["ref"].path)
     c.clear()
     try:
@@ -280,6 +292,7 @@ def run_reference(args, rank):
         "reads_per_s": gcups * 1e9 / full_cells_per_read,
         "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": first["cores"], "kind": "reference",
                          "parallel_efficiency": float(np.mean(effs)),
+                         "value_at_perfect_balance": gcups / max(float(np.mean(effs)), 1e-9),
                          "sample": first["sample"] + f"; each step = a fresh batch of {nreads} reads on the same profiles"},
         "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
