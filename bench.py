@@ -56,7 +56,7 @@ def measured_traffic():
     """DRAM bytes of the score pass of one step at the default workload, from the committed ncu
     capture (dram__bytes_read.sum + dram__bytes_write.sum; profiles/README.md).  None if absent."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic_v16.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic_v5.json")) as f:
             return float(json.load(f)["score_pass_dram_bytes_per_step"])
     except Exception:
         return None
