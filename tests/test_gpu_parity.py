@@ -322,9 +322,11 @@ def test_bench_workload_sample_matches_compiled_reference(reference, node_pool):
     """A K-stratified sample of bench.py's own workload (same generators, same seeds): every
     (profile, read) pair scored by the reference's viterbi.c on the host cores (oracle/_ref,
     multi-threaded scan loop) and by the GPU -- bit-identical null and alternative costs of the
-    first windows and the same hit count."""
+    first windows, the same hit count, and for every hit pair the decoded path of viterbi_path +
+    trellis_unzip step for step."""
     import os
     import bench
+    from oracle.oracle import ref_xtrans
     from deciphon_b200.device import Device
     from deciphon_b200.dcp_file import Profile
     seed, nprof_db, R, L = 20261018, 20000, 12, 2000
@@ -352,12 +354,22 @@ def test_bench_workload_sample_matches_compiled_reference(reference, node_pool):
         dev.set_reads(reads)
         dev.score_grid(0, len(pick), 0, R)
         nul, alt = dev.scores_fetch(len(pick) * R)
-        nhits = len(dev.hits_fetch())
+        hits = dev.hits_fetch()
+        nhits = len(hits)
         r = reference.scan(rprofs, reads, True, False, os.cpu_count() or 1, want_scores=True)
         # the reference scans the first window min(50 K, 100000, L) of each pair, like score_grid
         assert np.array_equal(_bits(nul), _bits(r["null"].reshape(-1)))
         assert np.array_equal(_bits(alt), _bits(r["alt"].reshape(-1)))
         d = r["alt"].reshape(-1) - r["null"].reshape(-1)  # lrt >= 0 <=> alt - null <= 0 (lrt.h:6-9)
         assert nhits == int(np.count_nonzero((d <= 0) & np.isfinite(d))) and nhits > 0
+        # paths of the hit pairs against the reference's own viterbi_path + trellis_unzip
+        win = np.minimum(np.minimum(sizes[pick] * 50, 100000), L)
+        rows = [(int(h // R), int(h % R), 0, int(win[h // R])) for h in hits]
+        talt, paths = dev.trace_pairs(_pairs(rows), True, False)
+        for (pi, si, _, wl), (ids, sz), ta in zip(rows, paths, talt):
+            rprofs[pi].set_xtrans(ref_xtrans(wl, True, False)[0])
+            rids, rsz = rprofs[pi].path(np.ascontiguousarray(reads[si][:wl]))
+            assert np.array_equal(ids, rids) and np.array_equal(sz, rsz), (pi, si)
+            assert _bits(np.asarray([ta]))[0] == _bits(alt[pi * R + si:pi * R + si + 1])[0]
     finally:
         dev.close()

@@ -246,3 +246,19 @@ def test_config5_long_read_full_traceback(device, oracle, node_pool):
         except StopIteration:
             pass
     assert nwin >= 5 + 9 and nhit >= 4  # K = 50 alone yields ~10 windows of 2,500 nt
+
+
+@pytest.mark.gpu
+def test_config2_and_config5_literal_against_the_compiled_reference(reference, node_pool):
+    """BASELINE.json configs 2 and 5 as bench.py times them (K = 3 x 1,000 reads of 1 kb in 150-nt
+    windows; one 24-kb read x profiles of 50..2000 nodes with full traceback) through dcp_scan_run,
+    against the reference's own scan loop (oracle/_ref): the same DP cells -- every window start
+    depends on the hits decoded before it -- and the same number of windows through the lrt gate."""
+    import argparse
+    import bench
+    args = argparse.Namespace(seed=20261018, tmp="")
+    gpu = bench.small_config_legs(args, node_pool)
+    cpu = bench.cpu_small_configs(args, node_pool, gpu)
+    for name in ("config2", "config5"):
+        assert gpu[name]["windows"] > 0 and cpu[name]["parity_with_gpu_leg"] is True, (name, gpu[name], cpu[name])
+    assert gpu["config2"]["windows"] >= 7000 and gpu["config5"]["lrt_windows"] >= 5 and gpu["config5"]["rows"] >= 5
