@@ -95,6 +95,7 @@ struct dcp_scan
   std::atomic<int> done_proteins{0};
   std::atomic<long> windows{0}, lrt_windows{0}; // cumulative: windows scored / with lrt >= 0 (dcpb200_scan_counter)
   double chunk_cells = 4e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
+  bool write_aminos = false; // DCP_WRITE_AMINOS: product_dir/aminos.fa, the hits' amino-acid sequences
 };
 
 namespace {
@@ -178,7 +179,25 @@ struct Row
   int seq_order;
   int window;
   std::string text;
+  std::string amino; // FASTA record of the hit's amino-acid sequence (only with DCP_WRITE_AMINOS)
 };
+
+// The amino-acid sequence the reference hands to HMMER for a hit (thread.c:168-180): the amino letter
+// of every non-mute step of the match column "<frag>,<state>,<codon>,<amino>;...".
+std::string amino_of_match(char const *text, size_t n)
+{
+  std::string out;
+  size_t i = 0;
+  while (i < n)
+  {
+    int commas = 0;
+    size_t j = i;
+    for (; j < n && text[j] != ';'; ++j)
+      if (text[j] == ',' && ++commas == 3 && j + 1 < n && text[j + 1] != ';') out.push_back(text[j + 1]);
+    i = j + 1;
+  }
+  return out;
+}
 
 struct Active
 { // window iteration state of one (profile, sequence), window.c:7-11
@@ -478,6 +497,7 @@ int dcp_scan_setup(struct dcp_scan *x, char const *dbfile, int port, int num_thr
   close_shards(x);
   if (char const *env = getenv("DCP_CHUNK_CELLS"))
     if (atof(env) > 0) x->chunk_cells = atof(env);
+  if (char const *env = getenv("DCP_WRITE_AMINOS")) x->write_aminos = env[0] && env[0] != '0';
 
   // partitions -> GPUs: min(num_threads, visible devices, DCP_GPU_COUNT), starting at DCP_GPU_DEVICE;
   // every GPU takes DCP_SHARDS_PER_GPU (default 2) shards when the database is large enough: while
@@ -682,7 +702,17 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
         std::string row(head);
         row.append(text.data() + toff[i], (size_t)(toff[i + 1] - toff[i]));
         row.push_back('\n');
-        rows->push_back(Row{gp, pr.seq, win_idx[i0 + i], std::move(row)});
+        std::string fasta;
+        if (x->write_aminos)
+        {
+          char tag[192];
+          snprintf(tag, sizeof tag, ">%ld/%d/%s window=[%d,%d) hit=[%d,%d)\n", sq.id, win_idx[i0 + i], pm.accession.c_str(),
+                   pr.start, pr.start + pr.len, hstart[i], hstop[i]);
+          fasta = tag;
+          fasta += amino_of_match(text.data() + toff[i], (size_t)(toff[i + 1] - toff[i]));
+          fasta.push_back('\n');
+        }
+        rows->push_back(Row{gp, pr.seq, win_idx[i0 + i], std::move(row), std::move(fasta)});
       }
       tm.lap(4);
       i0 = i1;
@@ -884,6 +914,15 @@ int dcp_scan_run(struct dcp_scan *x, struct dcp_batch *batch, char const *produc
     for (auto const &r : rs) ok = ok && fwrite(r.text.data(), 1, r.text.size(), fp) == r.text.size();
   }
   ok = (fclose(fp) == 0) && ok;
+  if (ok && x->write_aminos)
+  { // the sequences the reference sends to the HMMER daemon one hit at a time (hmmer.c:83-108), as ONE
+    // FASTA file in row order: the input of a single batched hmmscan / hmmsearch --cut_ga run
+    FILE *fa = fopen((dir + "/hmmer/aminos.fa").c_str(), "wb");
+    if (!fa) return DCP_EWRITEPROD;
+    for (auto const &rs : rows)
+      for (auto const &r : rs) ok = ok && fwrite(r.amino.data(), 1, r.amino.size(), fa) == r.amino.size();
+    ok = (fclose(fa) == 0) && ok;
+  }
   return ok ? 0 : DCP_EWRITEPROD;
 }
 

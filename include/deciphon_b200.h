@@ -20,7 +20,10 @@
  *   * HMMER daemon (c-core/hmmer.c, thread.c:185-203): the third-party client libraries are
  *     not part of this build.  `port <= 0` runs WITHOUT the HMMER confirmation stage: every
  *     window with lrt >= 0 and a B..E segment yields a row, `evalue` is written as 0 and no
- *     .h3r files are produced.  `port > 0` returns DCP_EH3CDIAL.
+ *     .h3r files are produced.  `port > 0` returns DCP_EH3CDIAL.  With $DCP_WRITE_AMINOS=1 the
+ *     amino-acid sequence of every row (what the reference sends to the daemon hit by hit,
+ *     thread.c:168-190) is written to <product_dir>/hmmer/aminos.fa in row order: the input of
+ *     ONE batched hmmscan --cut_ga run over all hits instead of a round trip per hit.
  *   * dcp_press_* (c-core/press.c): HMMER3 ASCII -> .dcp in the reference's current encoding
  *     (minifam.hmm -> 3,609,858 bytes, test_press.c:26); the frame-state emission tables are
  *     computed on the GPU.  entry_dist is occupancy-based (press.c:60).

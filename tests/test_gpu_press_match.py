@@ -269,3 +269,33 @@ def test_window_waves_over_the_c_abi_match_dcp_scan_run(tmp_path, node_pool):
     assert w["pairs"] > 0 and w["hits"] > 0  # later windows exist and some hold hits
     assert got["cells"] == want["cells"]
     assert len(idx) + w["hits"] == want["lrt_windows"] and len(sizes) * R + w["pairs"] == want["windows"]
+
+
+def test_batched_amino_fasta_for_the_hmmer_stage(tmp_path, golden_profiles, golden_reads, monkeypatch):
+    """DCP_WRITE_AMINOS=1: hmmer/aminos.fa holds, row by row, the amino-acid sequence the reference
+    would send to the HMMER daemon for that hit (thread.c:168-190: the amino letters of the non-mute
+    steps of the match) -- checked against the golden rows' own match columns."""
+    from deciphon_b200.dcp_file import write_dcp
+    from deciphon_b200.scan import Batch, Scan, Sequence
+    path = str(tmp_path / "mini.dcp")
+    write_dcp(path, golden_profiles)
+    batch = Batch()
+    for r in golden_reads["consensus_fna"]:
+        batch.add(Sequence(r["id"], r["name"], r["data"]))
+    monkeypatch.setenv("DCP_WRITE_AMINOS", "1")
+    with Scan(path, 0, 1, True, False, False) as scan:
+        scan.run(str(tmp_path / "snap"), batch)
+    rows = [l.split("\t") for l in (tmp_path / "snap" / "products.tsv").read_text().splitlines()[1:]]
+    fa = (tmp_path / "snap" / "hmmer" / "aminos.fa").read_text().splitlines()
+    assert len(fa) == 2 * len(rows) and len(rows) >= 3
+    golden = {(l.split("\t")[0], l.split("\t")[7]): l.split("\t")[11]
+              for l in open(os.path.join(GOLDEN, "snap_products.tsv")).read().splitlines()[1:]}
+    seen = 0
+    for row, head, seq in zip(rows, fa[0::2], fa[1::2]):
+        assert head.startswith(f">{row[0]}/{row[1]}/{row[7]} ") and f"hit=[{row[5]},{row[6]})" in head
+        want = "".join(step.split(",")[3] for step in row[11].split(";") if step.split(",")[3])
+        assert seq == want and len(seq) > 100
+        if (row[0], row[7]) in golden:
+            assert seq == "".join(st.split(",")[3] for st in golden[(row[0], row[7])].split(";") if st.split(",")[3])
+            seen += 1
+    assert seen == 3
