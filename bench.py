@@ -389,6 +389,7 @@ def plugin_leg(args, world, sizes, pool, nodes_of, reads, R, nsteps_total):
         return {"value": d["cells"] / secs / 1e9, "unit": "GCUPS", "seconds": secs, "cells": d["cells"],
                 "h2d_bytes_per_step": int(d["h2d_bytes"] / args.steps), "d2h_bytes_per_step": int(d["d2h_bytes"] / args.steps),
                 "launches": int(d["launches"]), "windows": int(d["windows"]), "lrt_windows": int(d["lrt_windows"]),
+                "replanned_windows": int(d["speculative_windows"]),
                 "reads_per_s": args.steps * R / secs, "gpus": gpus, "shards": shards, "profiles": nprof,
                 "dcp_bytes": info["bytes"], "dcp_write_s": write_s, "setup_s": setup_s,
                 "rows_last_step": tsv.count(b"\n") - 1, "tsv_bytes_last_step": len(tsv),
@@ -452,6 +453,7 @@ def small_config_legs(args, pool):
             res[name] = {"workload": text, "gcups": cells / secs / 1e9, "reads_per_s": len(reads) / secs, "ms_per_run": 1e3 * secs,
                          "cells": cells, "windows": int((c1["windows"] - c0["windows"]) / reps),
                          "lrt_windows": int((c1["lrt_windows"] - c0["lrt_windows"]) / reps), "rows": rows,
+                         "replanned_windows": int((c1["speculative_windows"] - c0["speculative_windows"]) / reps),
                          "launches_per_run": int((c1["launches"] - c0["launches"]) / reps),
                          "api": "dcp_scan_run (libdeciphon_b200.so), host strings in, products.tsv out, 1 GPU"}
     finally:

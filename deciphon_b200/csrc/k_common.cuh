@@ -21,7 +21,7 @@ cudaError_t launch_row_t(StripArgs const &a, int sm_count, cudaStream_t st)
   return cudaGetLastError();
 }
 
-// Q = 5..8 switch for one (SEG, MODE, DUMP)
+// Q = 5, 6, 8 switch for one (SEG, MODE, DUMP); layout_shape never hands a single-warp shape Q = 7
 template <int SEG, int MODE, bool DUMP>
 cudaError_t launch_row_q58(int Q, StripArgs const &a, int sm_count, cudaStream_t st)
 {
@@ -29,7 +29,6 @@ cudaError_t launch_row_q58(int Q, StripArgs const &a, int sm_count, cudaStream_t
   {
   case 5: return launch_row_t<5, SEG, MODE, DUMP>(a, sm_count, st);
   case 6: return launch_row_t<6, SEG, MODE, DUMP>(a, sm_count, st);
-  case 7: return launch_row_t<7, SEG, MODE, DUMP>(a, sm_count, st);
   case 8: return launch_row_t<8, SEG, MODE, DUMP>(a, sm_count, st);
   default: return cudaErrorInvalidValue;
   }

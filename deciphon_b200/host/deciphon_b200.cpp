@@ -30,7 +30,9 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <fcntl.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <thread>
 #include <vector>
 
@@ -94,6 +96,8 @@ struct dcp_scan
   std::atomic<bool> interrupted{false};
   std::atomic<int> done_proteins{0};
   std::atomic<long> windows{0}, lrt_windows{0}; // cumulative: windows scored / with lrt >= 0 (dcpb200_scan_counter)
+  std::atomic<long> speculative_windows{0};     // planned and scored, then re-planned after a hit changed the chain
+  std::atomic<long long> cells{0};              // DP cells of the committed windows
   double chunk_cells = 4e11; // DP cells of first windows per chunk (DCP_CHUNK_CELLS)
   bool write_aminos = false; // DCP_WRITE_AMINOS: product_dir/aminos.fa, the hits' amino-acid sequences
 };
@@ -612,8 +616,10 @@ int dcpb200_scan_num_shards(struct dcp_scan const *x) { return x ? (int)x->shard
 double dcpb200_scan_counter(struct dcp_scan const *x, int what)
 {
   if (!x) return 0;
+  if (what == 3) return (double)x->cells;
   if (what == 4) return (double)x->windows;
   if (what == 5) return (double)x->lrt_windows;
+  if (what == 6) return (double)x->speculative_windows;
   double v = 0;
   for (auto const &sh : x->shards) v += dcpgpu_counter(sh.gpu, what);
   return v;
@@ -745,6 +751,7 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
     std::vector<int64_t> hit((size_t)nhits);
     if (nhits && (rc = dcpgpu_hits_fetch(gpu, nhits, hit.data(), &nhits))) return map_gpu_error(rc);
     x->windows += (long)P * S;
+    x->cells += (long long)cells; // first windows of the chunk (profile_cells above)
     x->lrt_windows += (long)nhits;
     std::vector<float> nul0, alt0;
     if (nhits)
@@ -785,19 +792,28 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
     tm.lap(5);
     if ((rc = process_hits(hp, widx, hn, ha, owner))) return rc;
 
-    // waves 1..: explicit windows of the pairs that are still active
+    // Later windows.  A pair's next window depends on the hit found in the previous one only
+    // through last_hit_pos (window.c:13-37, thread.c:162), and most windows hold no hit: every
+    // round PLANS each active pair's whole remaining chain of windows as if none of them had a
+    // hit, scores them all in one pass, commits every pair's windows up to and including its first
+    // one that passes the lrt gate, traces those, and replans from there.  Rounds = 1 + the largest
+    // number of gate-passing windows of a pair, instead of one GPU pass per window index.
     while (!active.empty() && !x->interrupted)
     {
-      std::vector<Active> next;
       std::vector<dcpgpu_pair> wp;
-      for (auto &a : active)
+      std::vector<int> pidx;                            // window index of every planned window
+      std::vector<size_t> first(active.size() + 1, 0);  // planned windows of active[i]: [first[i], first[i+1])
+      for (size_t i = 0; i < active.size(); ++i)
       {
-        int const len = (int)(offsets[(size_t)a.seq + 1] - offsets[(size_t)a.seq]);
-        if (window_next(a, len, x->profiles[(size_t)(sh.p0 + a.profile)].K))
+        Active t = active[i];
+        int const len = (int)(offsets[(size_t)t.seq + 1] - offsets[(size_t)t.seq]);
+        int const K = x->profiles[(size_t)(sh.p0 + t.profile)].K;
+        while (window_next(t, len, K))
         {
-          wp.push_back(dcpgpu_pair{a.profile, a.seq, a.start, a.stop - a.start});
-          next.push_back(a);
+          wp.push_back(dcpgpu_pair{t.profile, t.seq, t.start, t.stop - t.start});
+          pidx.push_back(t.idx);
         }
+        first[i + 1] = wp.size();
       }
       if (wp.empty()) break;
       std::vector<float> nulc(wp.size()), altc(wp.size());
@@ -805,22 +821,51 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
       if ((rc = dcpgpu_score_pairs(gpu, (int64_t)wp.size(), wp.data(), flags, nulc.data(), altc.data())))
         return map_gpu_error(rc);
       tm.lap(6);
-      std::vector<dcpgpu_pair> hp2;
-      std::vector<int> widx2;
-      std::vector<float> hn2, ha2;
-      std::vector<Active *> owner2;
-      for (size_t i = 0; i < wp.size(); ++i)
+      std::vector<Active> next;
+      std::vector<size_t> gate; // planned index of the gate-passing window of next[j]
+      next.reserve(active.size());
+      long committed = 0;
+      long long ccells = 0;
+      for (size_t i = 0; i < active.size(); ++i)
       {
-        float const lrt = -2 * ((-nulc[i]) - (-altc[i]));
-        if (!std::isfinite(lrt) || lrt < 0) continue; // thread.c:121
-        hp2.push_back(wp[i]);
-        widx2.push_back(next[i].idx);
-        hn2.push_back(nulc[i]);
-        ha2.push_back(altc[i]);
-        owner2.push_back(&next[i]);
+        int const Ki = x->profiles[(size_t)(sh.p0 + active[i].profile)].K;
+        size_t j = first[i];
+        for (; j < first[i + 1]; ++j)
+        {
+          float const lrt = -2 * ((-nulc[j]) - (-altc[j]));
+          if (std::isfinite(lrt) && lrt >= 0) break; // thread.c:121
+        }
+        if (j == first[i + 1])
+        { // no further candidate: the pair's chain ends here, every planned window stands
+          committed += (long)(first[i + 1] - first[i]);
+          for (size_t w = first[i]; w < first[i + 1]; ++w) ccells += (long long)wp[w].len * Ki;
+          continue;
+        }
+        committed += (long)(j - first[i] + 1);
+        for (size_t w = first[i]; w <= j; ++w) ccells += (long long)wp[w].len * Ki;
+        Active t = active[i]; // the committed state: window j (last_hit_pos carried over, window.c never resets it)
+        t.start = wp[j].start;
+        t.stop = wp[j].start + wp[j].len;
+        t.idx = pidx[j];
+        next.push_back(t);
+        gate.push_back(j);
       }
-      x->windows += (long)wp.size();
+      std::vector<dcpgpu_pair> hp2(next.size());
+      std::vector<int> widx2(next.size());
+      std::vector<float> hn2(next.size()), ha2(next.size());
+      std::vector<Active *> owner2(next.size());
+      for (size_t j = 0; j < next.size(); ++j)
+      {
+        hp2[j] = wp[gate[j]];
+        widx2[j] = pidx[gate[j]];
+        hn2[j] = nulc[gate[j]];
+        ha2[j] = altc[gate[j]];
+        owner2[j] = &next[j];
+      }
+      x->windows += committed;
+      x->cells += ccells;
       x->lrt_windows += (long)hp2.size();
+      x->speculative_windows += (long)wp.size() - committed;
       if ((rc = process_hits(hp2, widx2, hn2, ha2, owner2))) return rc;
       active.swap(next);
       if (shard_index == 0 && x->callback) x->callback(x->userdata);
@@ -900,20 +945,65 @@ int dcp_scan_run(struct dcp_scan *x, struct dcp_batch *batch, char const *produc
     if (r) return r;
 
   // product_close (product.c:34-87): header + the shards' rows in shard (= profile) order, each
-  // shard's rows in (profile, batch order, window) order
-  FILE *fp = fopen((dir + "/products.tsv").c_str(), "wb");
-  if (!fp) return DCP_EWRITEPROD;
-  bool ok = fputs("sequence\twindow\twindow_start\twindow_stop\thit\thit_start\thit_stop\tprofile\tabc\tlrt\tevalue\tmatch\n", fp) >= 0;
-  for (auto &rs : rows)
-  {
-    std::stable_sort(rs.begin(), rs.end(), [](Row const &a, Row const &b) {
+  // shard's rows in (profile, batch order, window) order.  The reference concatenates per-thread
+  // files; here every shard's thread sorts its rows and writes them at the shard's offset of the
+  // one file (pwrite), so the N shards' text (hundreds of MB per batch at 8 GPUs) goes out in parallel.
+  static char const header[] = "sequence\twindow\twindow_start\twindow_stop\thit\thit_start\thit_stop\tprofile\tabc\tlrt\tevalue\tmatch\n";
+  std::vector<size_t> bytes(W, 0);
+  auto sort_rows = [&](size_t i) {
+    std::stable_sort(rows[i].begin(), rows[i].end(), [](Row const &a, Row const &b) {
       if (a.profile != b.profile) return a.profile < b.profile;
       if (a.seq_order != b.seq_order) return a.seq_order < b.seq_order;
       return a.window < b.window;
     });
-    for (auto const &r : rs) ok = ok && fwrite(r.text.data(), 1, r.text.size(), fp) == r.text.size();
+    for (auto const &r : rows[i]) bytes[i] += r.text.size();
+  };
+  int const fd = open((dir + "/products.tsv").c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+  if (fd < 0) return DCP_EWRITEPROD;
+  std::vector<char> okv(W, 1);
+  auto write_rows = [&](size_t i, size_t offset) {
+    std::string buf;
+    buf.reserve(std::min<size_t>(bytes[i], size_t(8) << 20) + 65536);
+    auto flush = [&] {
+      size_t done = 0;
+      while (done < buf.size())
+      {
+        ssize_t const n = pwrite(fd, buf.data() + done, buf.size() - done, (off_t)(offset + done));
+        if (n <= 0) { okv[i] = 0; return; }
+        done += (size_t)n;
+      }
+      offset += buf.size();
+      buf.clear();
+    };
+    for (auto const &r : rows[i])
+    {
+      buf += r.text;
+      if (buf.size() >= (size_t(8) << 20)) flush();
+    }
+    flush();
+  };
+  bool ok = pwrite(fd, header, sizeof header - 1, 0) == (ssize_t)(sizeof header - 1);
+  if (W == 1)
+  {
+    sort_rows(0);
+    write_rows(0, sizeof header - 1);
   }
-  ok = (fclose(fp) == 0) && ok;
+  else
+  {
+    std::vector<std::thread> ts;
+    for (size_t i = 0; i < W; ++i) ts.emplace_back(sort_rows, i);
+    for (auto &t : ts) t.join();
+    ts.clear();
+    size_t off = sizeof header - 1;
+    for (size_t i = 0; i < W; ++i)
+    {
+      ts.emplace_back(write_rows, i, off);
+      off += bytes[i];
+    }
+    for (auto &t : ts) t.join();
+  }
+  for (char c : okv) ok = ok && c;
+  ok = (close(fd) == 0) && ok;
   if (ok && x->write_aminos)
   { // the sequences the reference sends to the HMMER daemon one hit at a time (hmmer.c:83-108), as ONE
     // FASTA file in row order: the input of a single batched hmmscan / hmmsearch --cut_ga run

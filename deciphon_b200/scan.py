@@ -147,7 +147,7 @@ class Scan:
     def counters(self) -> dict:
         """Cumulative H2D / D2H bytes, kernel launches and DP cells of this scan's GPU contexts, windows
         scored and windows that passed the lrt gate."""
-        names = ("h2d_bytes", "d2h_bytes", "launches", "cells", "windows", "lrt_windows")
+        names = ("h2d_bytes", "d2h_bytes", "launches", "cells", "windows", "lrt_windows", "speculative_windows")
         return {n: lib.dcpb200_scan_counter(self._cscan, i) for i, n in enumerate(names)}
 
     def free(self):

@@ -73,8 +73,10 @@ int dcpb200_db_info(char const *dbfile, int *num_proteins, long *total_core_size
 int dcpb200_scan_num_gpus(struct dcp_scan const *);
 int dcpb200_scan_num_shards(struct dcp_scan const *);
 /* Extension: cumulative counters summed over the shards' GPU contexts (dcpgpu_counter): 0 = bytes
- * copied host -> device, 1 = bytes copied device -> host, 2 = kernels launched, 3 = DP cells scored;
- * and of the scan itself: 4 = windows scored, 5 = windows with lrt >= 0 (thread.c:119-121). */
+ * copied host -> device, 1 = bytes copied device -> host, 2 = kernels launched; and of the scan
+ * itself: 3 = DP cells of the windows it scanned, 4 = those windows, 5 = the ones with lrt >= 0
+ * (thread.c:119-121), 6 = windows scored ahead of a hit that changed the chain and re-planned
+ * (extra work, not counted in 3 and 4). */
 double dcpb200_scan_counter(struct dcp_scan const *, int what);
 
 /* Error codes 1..80 are the reference's (c-core/deciphon.h:34-116); only the ones this

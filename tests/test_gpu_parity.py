@@ -214,14 +214,12 @@ def test_empty_and_invalid(device, golden_dev):
         device.score_pairs(_pairs([(base, 0, 0, 0)]))  # empty window (window.c BUG_ON)
 
 
-@pytest.mark.parametrize("segments", ["1", "0"])
-def test_chunked_strip_columns_and_slot_overflow(oracle, node_pool, monkeypatch, segments):
+def test_chunked_strip_columns_and_slot_overflow(oracle, node_pool, monkeypatch):
     """The two rarely taken host paths: boundary columns that do not fit their budget (strip
     classes take turns, chunk after chunk) and traced paths that outgrow their slot (rerun with
     exact sizes).  Both are forced through the documented environment hooks; results must not
     change."""
     from deciphon_b200.device import Device
-    monkeypatch.setenv("DCPGPU_SEGMENTS", segments)      # segmented profiles / uniform strips
     monkeypatch.setenv("DCPGPU_COL_BUDGET_MB", "1")      # 1 MiB: a few dozen columns per chunk
     monkeypatch.setenv("DCPGPU_LZ_SLACK", "-1000000")    # 4-step slots: every traced path overflows
     dev = Device(0)
@@ -277,8 +275,8 @@ def test_layout_variants_agree(node_pool, monkeypatch):
                             [2048, 2049, 256, 257, 128, 129, 512, 513, 33, 32]])
     nprof, R, L = len(sizes), 24, 900
     results = []
-    for env in ({}, {"DCPGPU_SUBWARP": "0"}, {"DCPGPU_SEGMENTS": "0"}):
-        for k in ("DCPGPU_SUBWARP", "DCPGPU_SEGMENTS"):
+    for env in ({}, {"DCPGPU_SUBWARP": "0"}):
+        for k in ("DCPGPU_SUBWARP",):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
