@@ -579,7 +579,7 @@ int prepare_segments(dcpgpu_ctx *ctx, bool grid, std::vector<std::pair<int, long
                      int maxlen, SegPlan *plan)
 {
   plan->grid = grid;
-  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 2;
+  plan->stride = (size_t)std::min(std::max(maxlen, 1), DCPGPU_MAX_WINDOW) + 3; // rows 0..L, read two rows ahead
   size_t chunk_entries = entries.size();
   {
     size_t fr = 0, tot = 0;

@@ -185,7 +185,7 @@ struct Partial
 template <int Q, int SEG, int MODE, bool DUMP, int J>
 __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EmRows<Q, SEG> const &em, float2 const *nulbg,
                                        uint32_t eight, uint32_t h, uint32_t hn, int sl, float NB, float EB, float JB, float4 &bnext,
-                                       Mail *slot, float &E, float &x, bool &ok, DumpRef<DUMP> const &dv, int l,
+                                       float4 &bnext2, Mail *slot, float &E, float &x, bool &ok, DumpRef<DUMP> const &dv, int l,
                                        bool in_window)
 {
   constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
@@ -193,12 +193,14 @@ __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EmRows<Q, SEG
   constexpr bool COL_OUT = MODE == ROW_FIRST || MODE == ROW_MID;
   constexpr bool SPEC_B = MODE != ROW_WHOLE;
 
-  // boundary of row l (requested during row l-1); request row l+1's
+  // boundary of row l (requested during row l-2: the column left L2 long ago and a DRAM round trip
+  // under load outlasts one row); request row l+2's
   float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
   if constexpr (HEAD_IN)
   {
     b = bnext;
-    bnext = __ldcg(reinterpret_cast<float4 const *>(slot + 1));
+    bnext = bnext2;
+    bnext2 = __ldcg(reinterpret_cast<float4 const *>(slot + 2));
   }
 
   // (A) finish row l: the t = 1 term needs P(l-1), Q(l-1); the t = 5 terms read the ring slot this
@@ -467,13 +469,17 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
     uint32_t const eight = (uint32_t)a.s.reads.eight;
     float E = CUDART_INF_F, x = CUDART_INF_F, Eres = CUDART_INF_F, xres = CUDART_INF_F;
     bool ok = true, okres = true;
-    float4 bnext = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F);
-    if constexpr (MODE == ROW_MID || MODE == ROW_LAST) bnext = __ldcg(reinterpret_cast<float4 const *>(col + 1));
+    float4 bnext = make_float4(CUDART_INF_F, CUDART_INF_F, CUDART_INF_F, CUDART_INF_F), bnext2 = bnext;
+    if constexpr (MODE == ROW_MID || MODE == ROW_LAST)
+    {
+      bnext = __ldcg(reinterpret_cast<float4 const *>(col + 1));
+      bnext2 = __ldcg(reinterpret_cast<float4 const *>(col + 2));
+    }
 #define DCP_ROW(JJ_, I_)                                                                         \
   {                                                                                              \
     if (l > Lmax) break;                                                                         \
     uint32_t const hn = __ldg(hp + (I_) + 1);                                                    \
-    row_v2<Q, SEG, MODE, DUMP, JJ_>(s, pt, em, pd.nulbg, eight, h, hn, sl, NB, EB, JB, bnext, col + l, E, x, ok, dv, l,  \
+    row_v2<Q, SEG, MODE, DUMP, JJ_>(s, pt, em, pd.nulbg, eight, h, hn, sl, NB, EB, JB, bnext, bnext2, col + l, E, x, ok, dv, l,  \
                                     l <= L);                                                     \
     if (SEG != 32 && l == L)                                                                     \
     {                                                                                            \
