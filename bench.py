@@ -321,11 +321,12 @@ def to_text(x: np.ndarray) -> str:
     return np.frombuffer(b"ACGT", dtype=np.uint8)[x].tobytes().decode()
 
 
-def tmp_root(args, need_bytes: int):
-    """A fresh directory on a local file system with room for need_bytes, else None."""
+def tmp_root(args, need_bytes: int, small: bool = False):
+    """A fresh directory on a local file system with room for need_bytes, else None.  small: a few MB
+    of files -- memory-backed first, so that no disk traffic of another leg gets into their timing."""
     import shutil
     import tempfile
-    cands = [args.tmp] if args.tmp else ["/tmp", "/var/tmp", "/dev/shm"]
+    cands = [args.tmp] if args.tmp else (["/dev/shm", "/tmp", "/var/tmp"] if small else ["/tmp", "/var/tmp", "/dev/shm"])
     for c in cands:
         try:
             os.makedirs(c, exist_ok=True)
@@ -425,7 +426,7 @@ def small_config_legs(args, pool):
 
     from deciphon_b200.dcp_file import write_dcp
     from deciphon_b200.scan import Batch, Scan, Sequence
-    root = tmp_root(args, 64 << 20)
+    root = tmp_root(args, 64 << 20, small=True)
     res = {}
     if root is None:
         return res
@@ -670,15 +671,15 @@ def run_b200(args, rank, local_rank, world):
     if world > 1:
         dist.barrier(group=cpu_group)  # every rank has released its GPU memory
     if rank == 0 and not args.no_plugin:
-        try:
-            plugin = plugin_leg(args, world, sizes, pool, nodes_of, reads, R, nsteps_total)
-        except Exception as e:  # report, do not lose the measured legs
-            plugin = {"unavailable": f"{type(e).__name__}: {e}"}
-        if world == 1:
+        if world == 1:  # (before the 24-GB database file is written: its write-back would stall their small files)
             try:
                 small = small_config_legs(args, pool)
             except Exception as e:
                 small = {"unavailable": f"{type(e).__name__}: {e}"}
+        try:
+            plugin = plugin_leg(args, world, sizes, pool, nodes_of, reads, R, nsteps_total)
+        except Exception as e:  # report, do not lose the measured legs
+            plugin = {"unavailable": f"{type(e).__name__}: {e}"}
     if world > 1:
         dist.barrier(group=cpu_group)
 
