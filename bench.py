@@ -18,10 +18,11 @@ Prints ONE JSON line (rank 0).
              HBM: every window.c window of every pair (profiles of fewer than 40 nodes take two or
              three windows per 2,000-nt read), CUDA events, max over ranks.
   `e2e`      the same batches through the REFERENCE API, dcp_scan_setup / dcp_scan_run of
-             libdeciphon_b200.so (include/deciphon_b200.h): the database is a real .dcp file
-             written to local disk, reads are host strings in a dcp_batch, and every step ends
-             with its products.tsv on disk (encode, H2D, D2H, row formatting and file writing
-             inside the timed region).  At N > 1 one process drives the N GPUs as N profile
+             libdeciphon_b200.so (include/deciphon_b200.h): the database is a real .dcp file on a
+             local file system (/dev/shm when a third of the free RAM holds its 24.5 GB, else
+             /tmp), reads are host strings in a dcp_batch, and every step ends with its
+             products.tsv written (encode, H2D, D2H, row formatting and file writing inside the
+             timed region).  At N > 1 one process drives the N GPUs as N profile
              shards (num_threads = N), exactly what a caller of the reference API gets.
   `e2e_cabi` the same batches through the C ABI with host buffers (no row formatting).
   `roofline` the score kernels against the FP32 issue ceiling (and the best measured add/min mix).
@@ -321,12 +322,13 @@ def to_text(x: np.ndarray) -> str:
     return np.frombuffer(b"ACGT", dtype=np.uint8)[x].tobytes().decode()
 
 
-def tmp_root(args, need_bytes: int, small: bool = False):
-    """A fresh directory on a local file system with room for need_bytes, else None.  small: a few MB
-    of files -- memory-backed first, so that no disk traffic of another leg gets into their timing."""
+def tmp_root(args, need_bytes: int):
+    """A fresh directory on a local file system with room for need_bytes, else None."""
     import shutil
     import tempfile
-    cands = [args.tmp] if args.tmp else (["/dev/shm", "/tmp", "/var/tmp"] if small else ["/tmp", "/var/tmp", "/dev/shm"])
+    # memory-backed first (when a third of the available RAM holds it): the write-back of tens of GB to
+    # disk would otherwise run under the timed steps that follow
+    cands = [args.tmp] if args.tmp else ["/dev/shm", "/tmp", "/var/tmp"]
     for c in cands:
         try:
             os.makedirs(c, exist_ok=True)
@@ -426,7 +428,7 @@ def small_config_legs(args, pool):
 
     from deciphon_b200.dcp_file import write_dcp
     from deciphon_b200.scan import Batch, Scan, Sequence
-    root = tmp_root(args, 64 << 20, small=True)
+    root = tmp_root(args, 64 << 20)
     res = {}
     if root is None:
         return res
