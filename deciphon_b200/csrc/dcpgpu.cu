@@ -143,6 +143,8 @@ struct dcpgpu_ctx
   cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
   Mail *d_col = nullptr; // boundary columns of the one-strip-per-launch kernels
   size_t col_cap = 0;
+  int stage = 1; // DCPGPU_STAGE: profile-stationary CTAs with TMA-staged short-code rows (row_kernel.cuh):
+                 // 0 = never, 1 = the classes where it measured faster (Q = 5, 6 whole; first segments), 2 = also Q = 8 whole
   size_t col_budget = size_t(16) << 30; // DCPGPU_COL_BUDGET_MB: cap of the boundary columns (tests force chunking)
   long long lz_slack = 64;              // DCPGPU_LZ_SLACK: slack of a lazily walked path's slot (tests force the rerun)
   bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
@@ -519,7 +521,12 @@ int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
     sa.s = a;
     int const Q = cls <= 8 ? cls : 5 + (cls - 21) % 4;
     int const SEG = cls <= 8 ? 32 : cls <= 24 ? 16 : cls <= 28 ? 8 : 4;
-    e = launch_row(Q, SEG, ROW_WHOLE, DUMP, sa, ctx->sm_count, st);
+    // profile-stationary CTAs with TMA-staged short-code rows: measured +5 % at Q = 5, +2 % at Q = 6, -2 % at
+    // Q = 8 (172 KB of shared memory leave the 4-/5-mer rows 56 KB of L1): on for Q = 5, 6 (stage = 1)
+    if (!DUMP && SEG == 32 && !a.pairs && a.nseq >= 4 && ((ctx->stage == 1 && (Q == 5 || Q == 6)) || (ctx->stage == 2 && Q >= 5)))
+      e = launch_row_stage(Q, ROW_WHOLE, sa, ctx->sm_count, st);
+    else
+      e = launch_row(Q, SEG, ROW_WHOLE, DUMP, sa, ctx->sm_count, st);
   }
   else if (cls >= 9 && cls <= 20)
     e = launch_reg_multi(5 + (cls - 9) % 4, cls <= 12 ? 2 : cls <= 16 ? 4 : 8, DUMP, a, ctx->sm_count, st);
@@ -544,7 +551,8 @@ int tail_class(ProfileDesc const &g)
 int launch_segment(dcpgpu_ctx *ctx, int kind, StripArgs const &a, cudaStream_t st)
 {
   cudaError_t e;
-  if (kind == -2) e = launch_row(8, 32, ROW_FIRST, false, a, ctx->sm_count, st);
+  if (kind == -2 && ctx->stage && !a.s.pairs && a.s.nseq >= 4) e = launch_row_stage(8, ROW_FIRST, a, ctx->sm_count, st);
+  else if (kind == -2) e = launch_row(8, 32, ROW_FIRST, false, a, ctx->sm_count, st);
   else if (kind == -1) e = launch_row(8, 32, ROW_MID, false, a, ctx->sm_count, st);
   else if (kind >= 0 && kind < 16) e = launch_row(5 + kind % 4, 32 >> (kind / 4), ROW_LAST, false, a, ctx->sm_count, st);
   else return fail(ctx, DCPGPU_EINVAL, "bad segment kind");
@@ -934,6 +942,7 @@ int dcpgpu_open(dcpgpu_ctx **out, int device)
     ctx->subwarp = !(v && v[0] == '0');
     if ((v = std::getenv("DCPGPU_COL_BUDGET_MB")) && std::atoll(v) > 0) ctx->col_budget = (size_t)std::atoll(v) << 20;
     if ((v = std::getenv("DCPGPU_LZ_SLACK"))) ctx->lz_slack = std::atoll(v);
+    if ((v = std::getenv("DCPGPU_STAGE"))) ctx->stage = std::atoi(v);
   }
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

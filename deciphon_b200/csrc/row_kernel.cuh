@@ -82,14 +82,30 @@ __device__ __forceinline__ char const *mad_ptr(char const *base, uint32_t code, 
 #endif
 }
 
+// one probe of an mbarrier phase; the caller loops in C++ so that the control flow stays structured
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+
+constexpr int STAGE_ROWS = 84; // code rows of the 1-, 2- and 3-mers: contiguous at the head of em[1364][Kpad]
+
 // Emission rows of a profile striped over SEG lanes with Q nodes each (layout.cuh): per-lane base
 // pointers of the float4 / float2 / float chunks; a code row is base + code * ROWB + constant.
-template <int Q, int SEG>
+// STAGE: the 84 short-code rows are read from the CTA's shared-memory copy (same layout, staged by
+// one TMA bulk copy per profile), the 4-/5-mer rows from global memory as before.
+template <int Q, int SEG, bool STAGE = false>
 struct EmRows
 {
   static constexpr uint32_t ROWB = 4u * SEG * Q; // bytes per code row (Kpad = SEG * Q)
   static constexpr int N4 = Q / 4;
   char const *b4, *b2, *b1;
+  uint32_t s4, s2, s1; // shared-memory addresses of the same chunks (STAGE)
   uint32_t rowb; // == ROWB, as a run-time value (see mad_ptr)
   __device__ __forceinline__ uint32_t stride() const
   {
@@ -99,17 +115,36 @@ struct EmRows
     return ROWB;
 #endif
   }
-  __device__ __forceinline__ EmRows(float const *em, int sl, uint32_t rowb_) : rowb(rowb_)
+  __device__ __forceinline__ EmRows(float const *em, int sl, uint32_t rowb_, uint32_t stage = 0) : rowb(rowb_)
   {
     b4 = reinterpret_cast<char const *>(em) + (size_t)sl * 16;
     b2 = reinterpret_cast<char const *>(em + SEG * (N4 * 4)) + (size_t)sl * 8;
     b1 = reinterpret_cast<char const *>(em + SEG * (Q - 1)) + (size_t)sl * 4;
+    s4 = stage + (uint32_t)sl * 16u;
+    s2 = stage + 4u * SEG * (N4 * 4) + (uint32_t)sl * 8u;
+    s1 = stage + 4u * SEG * (Q - 1) + (uint32_t)sl * 4u;
   }
   // row of code OFF + idx
   template <int OFF>
   __device__ __forceinline__ void load(float (&e)[Q], uint32_t idx) const
   {
     constexpr uint32_t C = (uint32_t)OFF * ROWB;
+    if constexpr (STAGE && OFF < STAGE_ROWS)
+    {
+      uint32_t const r = idx * ROWB + C;
+      if constexpr (N4 > 0)
+      {
+#pragma unroll
+        for (int c = 0; c < N4; ++c)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(e[4 * c + 0]), "=f"(e[4 * c + 1]), "=f"(e[4 * c + 2]), "=f"(e[4 * c + 3])
+                       : "r"(s4 + r + (uint32_t)c * 16u * SEG));
+      }
+      if constexpr ((Q & 2) != 0)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(e[N4 * 4 + 0]), "=f"(e[N4 * 4 + 1]) : "r"(s2 + r));
+      if constexpr ((Q & 1) != 0) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(e[Q - 1]) : "r"(s1 + r));
+      return;
+    }
     if constexpr (N4 > 0)
     {
       char const *p = mad_ptr(b4, idx, stride());
@@ -182,8 +217,8 @@ struct Partial
 
 // One DP row l (J = l % 5).  h = history ending at nucleotide l-1 (codes of row l), hn = ending at
 // nucleotide l (codes of row l+1).
-template <int Q, int SEG, int MODE, bool DUMP, int J>
-__device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EmRows<Q, SEG> const &em, float2 const *nulbg,
+template <int Q, int SEG, int MODE, bool DUMP, int J, class EM>
+__device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EM const &em, float2 const *nulbg,
                                        uint32_t eight, uint32_t h, uint32_t hn, int sl, float NB, float EB, float JB, float4 &bnext,
                                        float4 &bnext2, Mail *slot, float &E, float &x, bool &ok, DumpRef<DUMP> const &dv, int l,
                                        bool in_window)
@@ -368,22 +403,81 @@ constexpr int row_min_blocks()
   return Q >= 6 ? 2 : Q >= 4 ? 3 : Q == 3 ? 4 : Q == 2 ? 5 : 6;
 }
 
-template <int Q, int SEG, int MODE, bool DUMP = false>
+// STAGE (SEG = 32, grid mode only): profile-stationary CTAs.  A CTA claims four reads of ONE profile at
+// a time (one per warp), and when the profile changes one elected thread stages its 84 short-code
+// emission rows -- contiguous at the head of the table -- into shared memory with a single TMA bulk
+// copy (cp.async.bulk + mbarrier complete_tx); rows then read them with LDS.128.
+template <int Q, int SEG, int MODE, bool DUMP = false, bool STAGE = false>
 __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, DUMP>()) score_row_kernel(StripArgs a)
 {
   constexpr int G = 32 / SEG;
   static_assert(!DUMP || MODE == ROW_WHOLE, "the value dump runs on whole profiles");
+  static_assert(!STAGE || SEG == 32, "staged rows: one pair per warp");
   int const lane = threadIdx.x & 31;
   int const seg = lane / SEG, sl = lane % SEG;
+  constexpr uint32_t STAGE_BYTES = (uint32_t)STAGE_ROWS * EmRows<Q, SEG>::ROWB;
+  [[maybe_unused]] uint32_t stage_base = 0, stage_bar = 0, stage_phase = 0;
+  [[maybe_unused]] int staged_profile = -1;
+  __shared__ unsigned long long s_item;
+  if constexpr (STAGE)
+  {
+    extern __shared__ __align__(128) unsigned char stage_mem[];
+    stage_base = tma::smem_u32(stage_mem);
+    stage_bar = stage_base + STAGE_BYTES;
+    if (threadIdx.x == 0)
+    {
+      tma::mbar_init(stage_bar, 1);
+      tma::fence_barrier_init();
+    }
+    __syncthreads();
+  }
 
   for (;;)
   {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(a.s.counter, (unsigned long long)G);
-    base = __shfl_sync(FULL_MASK, base, 0);
-    if (base >= a.s.nitems) break;
-    bool const active = base + seg < a.s.nitems;
-    unsigned long long const item = active ? base + seg : base; // idle segments shadow segment 0
+    unsigned long long item;
+    bool active;
+    if constexpr (STAGE)
+    {
+      __syncthreads(); // every warp is done with the previous claim: s_item and the staged rows may change
+      if (threadIdx.x == 0) s_item = atomicAdd(a.s.counter, 1ULL);
+      __syncthreads();
+      // (the broadcast tells the compiler the claim is warp-uniform: no divergence guards around the row's shuffles)
+      unsigned long long const claim = __shfl_sync(FULL_MASK, s_item, 0);
+      unsigned const quads = ((unsigned)a.s.nseq + ROW_WARPS - 1) / ROW_WARPS;
+      if (claim >= (a.s.nitems / (unsigned)a.s.nseq) * quads) break;
+      unsigned const cpi = (unsigned)(claim / quads), cq = (unsigned)(claim - (unsigned long long)cpi * quads);
+      // (the warp's index through a broadcast: the compiler then knows the pair, hence the row loop's
+      // trip count, is warp-uniform and puts no divergence guards around the row's shuffles)
+      int const csi = (int)(cq * ROW_WARPS) + __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
+      active = csi < a.s.nseq;
+      item = (unsigned long long)cpi * (unsigned)a.s.nseq + (active ? csi : 0);
+      int const cp = a.s.class_profiles[cpi];
+      if (cp != staged_profile)
+      {
+        ProfileDesc const cd = MODE == ROW_WHOLE ? a.s.profiles[cp] : a.segs[a.seg_first[cp] + a.level];
+        if (threadIdx.x == 0)
+        {
+          tma::mbar_arrive_expect_tx(stage_bar, STAGE_BYTES);
+          tma::bulk_g2s(stage_base, cd.em, STAGE_BYTES, stage_bar);
+        }
+        if (threadIdx.x == 0) // one waiter (a structured loop: no opaque branches inside inline asm), then a CTA
+          while (!mbar_try_wait(stage_bar, stage_phase)) {} // barrier: the compiler sees converged warps below
+        __syncthreads();
+        stage_phase ^= 1u;
+        staged_profile = cp;
+      }
+      // (a warp without a read of its own -- nseq not a multiple of four -- shadows read 0 of the profile
+      // and writes no result: no divergent control flow around the row's shuffles)
+    }
+    else
+    {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(a.s.counter, (unsigned long long)G);
+      base = __shfl_sync(FULL_MASK, base, 0);
+      if (base >= a.s.nitems) break;
+      active = base + seg < a.s.nitems;
+      item = active ? base + seg : base; // idle segments shadow segment 0
+    }
 
     int p, sq, start, L;
     long long oidx;
@@ -465,7 +559,7 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
     // history of row l = hist[first + l - 1]; rows before the window (t > l) meet +INF states only
     uint16_t const *hp = a.s.reads.hist + (a.s.reads.seq_word[sq] * 16 + start);
     uint32_t h = __ldg(hp);
-    EmRows<Q, SEG> const em(pd.em, sl, (uint32_t)pd.Kpad * 4u);
+    EmRows<Q, SEG, STAGE> const em(pd.em, sl, (uint32_t)pd.Kpad * 4u, stage_base);
     uint32_t const eight = (uint32_t)a.s.reads.eight;
     float E = CUDART_INF_F, x = CUDART_INF_F, Eres = CUDART_INF_F, xres = CUDART_INF_F;
     bool ok = true, okres = true;

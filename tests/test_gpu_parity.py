@@ -371,3 +371,35 @@ def test_bench_workload_sample_matches_compiled_reference(reference, node_pool):
             assert _bits(np.asarray([ta]))[0] == _bits(alt[pi * R + si:pi * R + si + 1])[0]
     finally:
         dev.close()
+
+
+@pytest.mark.parametrize("nseq", [4, 6, 9])
+def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, monkeypatch, nseq):
+    """score_grid runs the profile-stationary kernels (short-code rows staged in shared memory by a TMA
+    bulk copy, four reads of one profile per CTA) for one-warp profiles and first segments;
+    score_pairs runs the plain kernels.  Same pairs, bit-identical costs -- also when the number of
+    reads is not a multiple of four (a warp without a read of its own shadows another) and when
+    consecutive claims of a CTA change profile.  Checked against the oracle on a sample."""
+    from deciphon_b200.device import Device
+    monkeypatch.setenv("DCPGPU_STAGE", "2")  # every staged class, Q = 8 whole profiles included
+    rng = np.random.default_rng(1000 + nseq)
+    sizes = [129, 150, 160, 161, 180, 192, 200, 230, 256, 257, 300, 520, 700]
+    reads = [synth.random_read(rng, int(rng.integers(200, 700))) for _ in range(nseq)]
+    with Device(0) as dev:
+        profs = [synth.synth_profile(rng, K, node_pool) for K in sizes]
+        for p in profs:
+            dev.add_profile(p)
+        dev.set_reads(reads)
+        dev.score_grid(0, len(sizes), 0, nseq, True, False)
+        gn, ga = dev.scores_fetch(len(sizes) * nseq)
+        ghits = dev.hits_fetch()
+        rows = [(p, s, 0, min(len(reads[s]), 50 * sizes[p])) for p in range(len(sizes)) for s in range(nseq)]
+        pn, pa = dev.score_pairs(_pairs(rows), True, False)
+        assert np.array_equal(_bits(gn), _bits(pn)) and np.array_equal(_bits(ga), _bits(pa))
+        d = pa - pn
+        assert np.array_equal(ghits, np.nonzero((d <= 0) & np.isfinite(d))[0])
+        for p, s in ((0, 0), (5, nseq - 1), (8, 1), (11, nseq - 1)):
+            costs = profs[p].costs()
+            x = reads[s]
+            xt = oracle.xtrans(len(x), True, False)
+            assert _bits(ga[p * nseq + s:p * nseq + s + 1])[0] == _bits(oracle.alt(costs, xt, x).reshape(1))[0]
