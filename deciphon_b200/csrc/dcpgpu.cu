@@ -144,7 +144,8 @@ struct dcpgpu_ctx
   Mail *d_col = nullptr; // boundary columns of the one-strip-per-launch kernels
   size_t col_cap = 0;
   int stage = 1; // DCPGPU_STAGE: profile-stationary CTAs with TMA-staged short-code rows (row_kernel.cuh):
-                 // 0 = never, 1 = the classes where it measured faster (Q = 5, 6 whole; first segments), 2 = also Q = 8 whole
+                 // 0 = never, 1 = the classes where it measured faster (Q = 5, 6 whole profiles, every whole-warp
+                 // segment of the larger ones), 2 = also Q = 8 whole profiles
   size_t col_budget = size_t(16) << 30; // DCPGPU_COL_BUDGET_MB: cap of the boundary columns (tests force chunking)
   long long lz_slack = 64;              // DCPGPU_LZ_SLACK: slack of a lazily walked path's slot (tests force the rerun)
   bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
@@ -551,7 +552,12 @@ int tail_class(ProfileDesc const &g)
 int launch_segment(dcpgpu_ctx *ctx, int kind, StripArgs const &a, cudaStream_t st)
 {
   cudaError_t e;
-  if (kind == -2 && ctx->stage && !a.s.pairs && a.s.nseq >= 4) e = launch_row_stage(8, ROW_FIRST, a, ctx->sm_count, st);
+  // profile-stationary variants (grid mode): first / later full segments and whole-warp tails, each
+  // measured +0.5..2.5 % over the plain kernels (profiles/README.md)
+  bool const staged = ctx->stage && !a.s.pairs && a.s.nseq >= 4;
+  if (kind == -2 && staged) e = launch_row_stage(8, ROW_FIRST, a, ctx->sm_count, st);
+  else if (kind == -1 && staged) e = launch_row_stage(8, ROW_MID, a, ctx->sm_count, st);
+  else if (kind >= 0 && kind < 4 && kind != 2 && staged) e = launch_row_stage(5 + kind, ROW_LAST, a, ctx->sm_count, st);
   else if (kind == -2) e = launch_row(8, 32, ROW_FIRST, false, a, ctx->sm_count, st);
   else if (kind == -1) e = launch_row(8, 32, ROW_MID, false, a, ctx->sm_count, st);
   else if (kind >= 0 && kind < 16) e = launch_row(5 + kind % 4, 32 >> (kind / 4), ROW_LAST, false, a, ctx->sm_count, st);

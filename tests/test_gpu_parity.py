@@ -383,7 +383,7 @@ def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, monkeypat
     from deciphon_b200.device import Device
     monkeypatch.setenv("DCPGPU_STAGE", "2")  # every staged class, Q = 8 whole profiles included
     rng = np.random.default_rng(1000 + nseq)
-    sizes = [129, 150, 160, 161, 180, 192, 200, 230, 256, 257, 300, 520, 700]
+    sizes = [129, 150, 160, 161, 180, 192, 200, 230, 256, 257, 300, 400, 440, 520, 700, 760, 1000]  # every staged mode
     reads = [synth.random_read(rng, int(rng.integers(200, 700))) for _ in range(nseq)]
     with Device(0) as dev:
         profs = [synth.synth_profile(rng, K, node_pool) for K in sizes]
@@ -398,7 +398,7 @@ def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, monkeypat
         assert np.array_equal(_bits(gn), _bits(pn)) and np.array_equal(_bits(ga), _bits(pa))
         d = pa - pn
         assert np.array_equal(ghits, np.nonzero((d <= 0) & np.isfinite(d))[0])
-        for p, s in ((0, 0), (5, nseq - 1), (8, 1), (11, nseq - 1)):
+        for p, s in ((0, 0), (5, nseq - 1), (8, 1), (11, nseq - 1), (14, 2), (16, nseq - 1)):
             costs = profs[p].costs()
             x = reads[s]
             xt = oracle.xtrans(len(x), True, False)
