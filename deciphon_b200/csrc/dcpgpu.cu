@@ -143,9 +143,7 @@ struct dcpgpu_ctx
   cudaStream_t pinned = nullptr; // overrides the rotation (kernels that depend on each other)
   Mail *d_col = nullptr; // boundary columns of the one-strip-per-launch kernels
   size_t col_cap = 0;
-  int stage = 1; // DCPGPU_STAGE: profile-stationary CTAs with TMA-staged short-code rows (row_kernel.cuh):
-                 // 0 = never, 1 = the classes where it measured faster (Q = 5, 6 whole profiles, every whole-warp
-                 // segment of the larger ones), 2 = also Q = 8 whole profiles
+  int stage = 1; // DCPGPU_STAGE=0: never use the profile-stationary (TMA-staged) kernels of row_kernel.cuh
   size_t col_budget = size_t(16) << 30; // DCPGPU_COL_BUDGET_MB: cap of the boundary columns (tests force chunking)
   long long lz_slack = 64;              // DCPGPU_LZ_SLACK: slack of a lazily walked path's slot (tests force the rerun)
   bool subwarp = true;           // DCPGPU_SUBWARP=0: profiles of <= 128 nodes keep a whole warp (A/B switch)
@@ -522,9 +520,9 @@ int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
     sa.s = a;
     int const Q = cls <= 8 ? cls : 5 + (cls - 21) % 4;
     int const SEG = cls <= 8 ? 32 : cls <= 24 ? 16 : cls <= 28 ? 8 : 4;
-    // profile-stationary CTAs with TMA-staged short-code rows: measured +5 % at Q = 5, +2 % at Q = 6, -2 % at
-    // Q = 8 (172 KB of shared memory leave the 4-/5-mer rows 56 KB of L1): on for Q = 5, 6 (stage = 1)
-    if (!DUMP && SEG == 32 && !a.pairs && a.nseq >= 4 && ((ctx->stage == 1 && (Q == 5 || Q == 6)) || (ctx->stage == 2 && Q >= 5)))
+    // profile-stationary CTAs with the short-code rows and the {null, background} table staged in shared
+    // memory by TMA: measured +4..10 % over the plain kernels for every whole-warp shape (profiles/README.md)
+    if (!DUMP && ctx->stage && SEG == 32 && Q >= 5 && !a.pairs && a.nseq >= 4)
       e = launch_row_stage(Q, ROW_WHOLE, sa, ctx->sm_count, st);
     else
       e = launch_row(Q, SEG, ROW_WHOLE, DUMP, sa, ctx->sm_count, st);

@@ -27,7 +27,7 @@ template <int Q, int MODE>
 cudaError_t launch_row_stage_t(StripArgs const &a, int sm_count, cudaStream_t st)
 {
   constexpr int T = 32 * ROW_WARPS;
-  constexpr size_t SMEM = (size_t)STAGE_ROWS * EmRows<Q, 32>::ROWB + 16;
+  constexpr size_t SMEM = (size_t)STAGE_ROWS * EmRows<Q, 32>::ROWB + (size_t)stage_nulbg_codes<Q>() * 8 + 16;
   if (a.s.pairs || a.s.nseq <= 0) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(score_row_kernel<Q, 32, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
   if (e != cudaSuccess) return e;

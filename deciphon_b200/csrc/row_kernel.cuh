@@ -42,7 +42,15 @@ namespace dcp {
 
 enum RowMode { ROW_WHOLE = 0, ROW_FIRST = 1, ROW_MID = 2, ROW_LAST = 3 };
 
-constexpr int ROW_WARPS = 4;         // warps per CTA, each with its own pair(s)
+constexpr int ROW_WARPS = 4;
+// The staged kernels also keep the profile's {null, background} table (float2 per code) in shared
+// memory: all 1364 codes where that fits beside the rows at the kernel's CTAs per SM, the 340 codes of
+// the 1..4-mers at Q = 6 (3 CTAs x (64.5 + 10.9 + 1) KB would exceed the SM's 227 KB).
+template <int Q>
+__host__ __device__ constexpr int stage_nulbg_codes()
+{
+  return Q == 6 ? 340 : NCODES;
+}         // warps per CTA, each with its own pair(s)
 constexpr int HIST_SLACK = 100032;   // u16 entries past the last read (a sub-warp lane runs to its warp's longest window)
 
 // ---- integer three-input min on non-negative floats -------------------------------------------
@@ -93,6 +101,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
   return ok != 0;
 }
 
+template <int OFF>
+__device__ __forceinline__ float2 ld_nulbg(float2 const *nulbg, uint32_t idx, uint32_t eight);
+
 constexpr int STAGE_ROWS = 84; // code rows of the 1-, 2- and 3-mers: contiguous at the head of em[1364][Kpad]
 
 // Emission rows of a profile striped over SEG lanes with Q nodes each (layout.cuh): per-lane base
@@ -106,6 +117,7 @@ struct EmRows
   static constexpr int N4 = Q / 4;
   char const *b4, *b2, *b1;
   uint32_t s4, s2, s1; // shared-memory addresses of the same chunks (STAGE)
+  uint32_t snb;        // shared-memory address of the staged {null, background} table, 0 = not staged
   uint32_t rowb; // == ROWB, as a run-time value (see mad_ptr)
   __device__ __forceinline__ uint32_t stride() const
   {
@@ -115,7 +127,8 @@ struct EmRows
     return ROWB;
 #endif
   }
-  __device__ __forceinline__ EmRows(float const *em, int sl, uint32_t rowb_, uint32_t stage = 0) : rowb(rowb_)
+  __device__ __forceinline__ EmRows(float const *em, int sl, uint32_t rowb_, uint32_t stage = 0, uint32_t stage_nb = 0)
+      : snb(stage_nb), rowb(rowb_)
   {
     b4 = reinterpret_cast<char const *>(em) + (size_t)sl * 16;
     b2 = reinterpret_cast<char const *>(em + SEG * (N4 * 4)) + (size_t)sl * 8;
@@ -123,6 +136,19 @@ struct EmRows
     s4 = stage + (uint32_t)sl * 16u;
     s2 = stage + 4u * SEG * (N4 * 4) + (uint32_t)sl * 8u;
     s1 = stage + 4u * SEG * (Q - 1) + (uint32_t)sl * 4u;
+  }
+  // {null, background} emission costs of code OFF + idx
+  template <int OFF>
+  __device__ __forceinline__ float2 nulbg(float2 const *table, uint32_t idx, uint32_t eight) const
+  {
+    if constexpr (STAGE && OFF < stage_nulbg_codes<Q>())
+    {
+      float2 v;
+      asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(snb + idx * 8u + (uint32_t)OFF * 8u));
+      return v;
+    }
+    else
+      return ld_nulbg<OFF>(table, idx, eight);
   }
   // row of code OFF + idx
   template <int OFF>
@@ -243,8 +269,8 @@ __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EM const &em,
   float M[Q], I[Q];
   float xacc;
   {
-    float2 const nb1 = ld_nulbg<0>(nulbg, h & 3u, eight);
-    float2 const nb5 = ld_nulbg<340>(nulbg, h & 1023u, eight);
+    float2 const nb1 = em.template nulbg<0>(nulbg, h & 3u, eight);
+    float2 const nb5 = em.template nulbg<340>(nulbg, h & 1023u, eight);
     float e[Q];
     em.template load<0>(e, h & 3u);
 #pragma unroll
@@ -262,8 +288,8 @@ __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EM const &em,
   E = e;
 
   // emission rows of row l+1 for t = 2..5
-  float2 const nb2 = ld_nulbg<4>(nulbg, hn & 15u, eight), nb3 = ld_nulbg<20>(nulbg, hn & 63u, eight),
-               nb4 = ld_nulbg<84>(nulbg, hn & 255u, eight);
+  float2 const nb2 = em.template nulbg<4>(nulbg, hn & 15u, eight), nb3 = em.template nulbg<20>(nulbg, hn & 63u, eight),
+               nb4 = em.template nulbg<84>(nulbg, hn & 255u, eight);
   float e2[Q], e3[Q], e4[Q], e5[Q];
   em.template load<4>(e2, hn & 15u);
   em.template load<20>(e3, hn & 63u);
@@ -416,6 +442,7 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
   int const lane = threadIdx.x & 31;
   int const seg = lane / SEG, sl = lane % SEG;
   constexpr uint32_t STAGE_BYTES = (uint32_t)STAGE_ROWS * EmRows<Q, SEG>::ROWB;
+  constexpr uint32_t STAGE_NB = (uint32_t)stage_nulbg_codes<Q>() * 8u;
   [[maybe_unused]] uint32_t stage_base = 0, stage_bar = 0, stage_phase = 0;
   [[maybe_unused]] int staged_profile = -1;
   __shared__ unsigned long long s_item;
@@ -423,7 +450,7 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
   {
     extern __shared__ __align__(128) unsigned char stage_mem[];
     stage_base = tma::smem_u32(stage_mem);
-    stage_bar = stage_base + STAGE_BYTES;
+    stage_bar = stage_base + STAGE_BYTES + STAGE_NB;
     if (threadIdx.x == 0)
     {
       tma::mbar_init(stage_bar, 1);
@@ -457,8 +484,9 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
         ProfileDesc const cd = MODE == ROW_WHOLE ? a.s.profiles[cp] : a.segs[a.seg_first[cp] + a.level];
         if (threadIdx.x == 0)
         {
-          tma::mbar_arrive_expect_tx(stage_bar, STAGE_BYTES);
+          tma::mbar_arrive_expect_tx(stage_bar, STAGE_BYTES + STAGE_NB);
           tma::bulk_g2s(stage_base, cd.em, STAGE_BYTES, stage_bar);
+          tma::bulk_g2s(stage_base + STAGE_BYTES, cd.nulbg, STAGE_NB, stage_bar);
         }
         if (threadIdx.x == 0) // one waiter (a structured loop: no opaque branches inside inline asm), then a CTA
           while (!mbar_try_wait(stage_bar, stage_phase)) {} // barrier: the compiler sees converged warps below
@@ -559,7 +587,7 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
     // history of row l = hist[first + l - 1]; rows before the window (t > l) meet +INF states only
     uint16_t const *hp = a.s.reads.hist + (a.s.reads.seq_word[sq] * 16 + start);
     uint32_t h = __ldg(hp);
-    EmRows<Q, SEG, STAGE> const em(pd.em, sl, (uint32_t)pd.Kpad * 4u, stage_base);
+    EmRows<Q, SEG, STAGE> const em(pd.em, sl, (uint32_t)pd.Kpad * 4u, stage_base, stage_base + STAGE_BYTES);
     uint32_t const eight = (uint32_t)a.s.reads.eight;
     float E = CUDART_INF_F, x = CUDART_INF_F, Eres = CUDART_INF_F, xres = CUDART_INF_F;
     bool ok = true, okres = true;

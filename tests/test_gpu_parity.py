@@ -374,14 +374,14 @@ def test_bench_workload_sample_matches_compiled_reference(reference, node_pool):
 
 
 @pytest.mark.parametrize("nseq", [4, 6, 9])
-def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, monkeypatch, nseq):
-    """score_grid runs the profile-stationary kernels (short-code rows staged in shared memory by a TMA
-    bulk copy, four reads of one profile per CTA) for one-warp profiles and first segments;
+def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, nseq):
+    """score_grid runs the profile-stationary kernels (short-code rows and the null/background table
+    staged in shared memory by TMA bulk copies, four reads of one profile per CTA) for one-warp
+    profiles of more than 128 nodes and the whole-warp segments of larger ones;
     score_pairs runs the plain kernels.  Same pairs, bit-identical costs -- also when the number of
     reads is not a multiple of four (a warp without a read of its own shadows another) and when
     consecutive claims of a CTA change profile.  Checked against the oracle on a sample."""
     from deciphon_b200.device import Device
-    monkeypatch.setenv("DCPGPU_STAGE", "2")  # every staged class, Q = 8 whole profiles included
     rng = np.random.default_rng(1000 + nseq)
     sizes = [129, 150, 160, 161, 180, 192, 200, 230, 256, 257, 300, 400, 440, 520, 700, 760, 1000]  # every staged mode
     reads = [synth.random_read(rng, int(rng.integers(200, 700))) for _ in range(nseq)]
