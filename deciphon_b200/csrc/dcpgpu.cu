@@ -522,8 +522,8 @@ int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
     int const SEG = cls <= 8 ? 32 : cls <= 24 ? 16 : cls <= 28 ? 8 : 4;
     // profile-stationary CTAs with the short-code rows and the {null, background} table staged in shared
     // memory by TMA: measured +4..10 % over the plain kernels for every whole-warp shape (profiles/README.md)
-    if (!DUMP && ctx->stage && SEG == 32 && Q >= 5 && !a.pairs && a.nseq >= 4)
-      e = launch_row_stage(Q, ROW_WHOLE, sa, ctx->sm_count, st);
+    if (!DUMP && ctx->stage && Q >= 5 && !a.pairs && a.nseq >= 4 * (32 / SEG))
+      e = launch_row_stage(Q, SEG, ROW_WHOLE, sa, ctx->sm_count, st);
     else
       e = launch_row(Q, SEG, ROW_WHOLE, DUMP, sa, ctx->sm_count, st);
   }
@@ -553,9 +553,10 @@ int launch_segment(dcpgpu_ctx *ctx, int kind, StripArgs const &a, cudaStream_t s
   // profile-stationary variants (grid mode): first / later full segments and whole-warp tails, each
   // measured +0.5..2.5 % over the plain kernels (profiles/README.md)
   bool const staged = ctx->stage && !a.s.pairs && a.s.nseq >= 4;
-  if (kind == -2 && staged) e = launch_row_stage(8, ROW_FIRST, a, ctx->sm_count, st);
-  else if (kind == -1 && staged) e = launch_row_stage(8, ROW_MID, a, ctx->sm_count, st);
-  else if (kind >= 0 && kind < 4 && kind != 2 && staged) e = launch_row_stage(5 + kind, ROW_LAST, a, ctx->sm_count, st);
+  if (kind == -2 && staged) e = launch_row_stage(8, 32, ROW_FIRST, a, ctx->sm_count, st);
+  else if (kind == -1 && staged) e = launch_row_stage(8, 32, ROW_MID, a, ctx->sm_count, st);
+  else if (kind >= 0 && kind < 16 && kind % 4 != 2 && ctx->stage && !a.s.pairs && a.s.nseq >= 4 * (1 << (kind / 4)))
+    e = launch_row_stage(5 + kind % 4, 32 >> (kind / 4), ROW_LAST, a, ctx->sm_count, st);
   else if (kind == -2) e = launch_row(8, 32, ROW_FIRST, false, a, ctx->sm_count, st);
   else if (kind == -1) e = launch_row(8, 32, ROW_MID, false, a, ctx->sm_count, st);
   else if (kind >= 0 && kind < 16) e = launch_row(5 + kind % 4, 32 >> (kind / 4), ROW_LAST, false, a, ctx->sm_count, st);

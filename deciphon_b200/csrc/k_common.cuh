@@ -23,23 +23,23 @@ cudaError_t launch_row_t(StripArgs const &a, int sm_count, cudaStream_t st)
 
 // Profile-stationary variant (grid mode, one pair per warp): the 84 short-code rows of the CTA's
 // current profile live in dynamic shared memory (+ 16 bytes for the mbarrier of the TMA bulk copy).
-template <int Q, int MODE>
+template <int Q, int SEG, int MODE>
 cudaError_t launch_row_stage_t(StripArgs const &a, int sm_count, cudaStream_t st)
 {
-  constexpr int T = 32 * ROW_WARPS;
-  constexpr size_t SMEM = (size_t)STAGE_ROWS * EmRows<Q, 32>::ROWB + (size_t)stage_nulbg_codes<Q>() * 8 + 16;
+  constexpr int T = 32 * ROW_WARPS, PER_CLAIM = ROW_WARPS * (32 / SEG);
+  constexpr size_t SMEM = (size_t)STAGE_ROWS * EmRows<Q, SEG>::ROWB + (size_t)stage_nulbg_codes<Q>() * 8 + 16;
   if (a.s.pairs || a.s.nseq <= 0) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(score_row_kernel<Q, 32, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  cudaError_t e = cudaFuncSetAttribute(score_row_kernel<Q, SEG, MODE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
   if (e != cudaSuccess) return e;
   int per_sm = 0;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_row_kernel<Q, 32, MODE, false, true>, T, SMEM);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_row_kernel<Q, SEG, MODE, false, true>, T, SMEM);
   if (e != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  unsigned long long const quads = ((unsigned long long)a.s.nseq + ROW_WARPS - 1) / ROW_WARPS;
+  unsigned long long const quads = ((unsigned long long)a.s.nseq + PER_CLAIM - 1) / PER_CLAIM;
   unsigned long long const want = (a.s.nitems / (unsigned long long)a.s.nseq) * quads;
   unsigned const grid = (unsigned)std::min<unsigned long long>(want, (unsigned long long)per_sm * sm_count);
   if (grid == 0) return cudaSuccess;
-  score_row_kernel<Q, 32, MODE, false, true><<<grid, T, SMEM, st>>>(a);
+  score_row_kernel<Q, SEG, MODE, false, true><<<grid, T, SMEM, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -59,6 +59,6 @@ cudaError_t launch_row_q58(int Q, StripArgs const &a, int sm_count, cudaStream_t
 cudaError_t launch_row_whole32(int Q, bool dump, StripArgs const &a, int sm_count, cudaStream_t st);
 cudaError_t launch_row_sub(int Q, int SEG, bool dump, StripArgs const &a, int sm_count, cudaStream_t st);
 cudaError_t launch_row_seg(int Q, int SEG, int mode, StripArgs const &a, int sm_count, cudaStream_t st);
-cudaError_t launch_row_stage(int Q, int mode, StripArgs const &a, int sm_count, cudaStream_t st);
+cudaError_t launch_row_stage(int Q, int SEG, int mode, StripArgs const &a, int sm_count, cudaStream_t st);
 
 } // namespace dcp

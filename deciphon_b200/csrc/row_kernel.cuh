@@ -429,16 +429,16 @@ constexpr int row_min_blocks()
   return Q >= 6 ? 2 : Q >= 4 ? 3 : Q == 3 ? 4 : Q == 2 ? 5 : 6;
 }
 
-// STAGE (SEG = 32, grid mode only): profile-stationary CTAs.  A CTA claims four reads of ONE profile at
-// a time (one per warp), and when the profile changes one elected thread stages its 84 short-code
-// emission rows -- contiguous at the head of the table -- into shared memory with a single TMA bulk
-// copy (cp.async.bulk + mbarrier complete_tx); rows then read them with LDS.128.
+// STAGE (grid mode only): profile-stationary CTAs.  A CTA claims 4 x (32 / SEG) reads of ONE profile at a
+// time (one per lane group), and when the profile changes one elected thread stages its 84 short-code
+// emission rows -- contiguous at the head of the table -- and its {null, background} table into shared
+// memory with TMA bulk copies (cp.async.bulk + mbarrier complete_tx); rows then read them with LDS and
+// 32-bit addresses.
 template <int Q, int SEG, int MODE, bool DUMP = false, bool STAGE = false>
 __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, DUMP>()) score_row_kernel(StripArgs a)
 {
   constexpr int G = 32 / SEG;
   static_assert(!DUMP || MODE == ROW_WHOLE, "the value dump runs on whole profiles");
-  static_assert(!STAGE || SEG == 32, "staged rows: one pair per warp");
   int const lane = threadIdx.x & 31;
   int const seg = lane / SEG, sl = lane % SEG;
   constexpr uint32_t STAGE_BYTES = (uint32_t)STAGE_ROWS * EmRows<Q, SEG>::ROWB;
@@ -470,12 +470,13 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
       __syncthreads();
       // (the broadcast tells the compiler the claim is warp-uniform: no divergence guards around the row's shuffles)
       unsigned long long const claim = __shfl_sync(FULL_MASK, s_item, 0);
-      unsigned const quads = ((unsigned)a.s.nseq + ROW_WARPS - 1) / ROW_WARPS;
+      constexpr unsigned PER_CLAIM = ROW_WARPS * G; // reads of the profile a CTA takes at a time
+      unsigned const quads = ((unsigned)a.s.nseq + PER_CLAIM - 1) / PER_CLAIM;
       if (claim >= (a.s.nitems / (unsigned)a.s.nseq) * quads) break;
       unsigned const cpi = (unsigned)(claim / quads), cq = (unsigned)(claim - (unsigned long long)cpi * quads);
       // (the warp's index through a broadcast: the compiler then knows the pair, hence the row loop's
       // trip count, is warp-uniform and puts no divergence guards around the row's shuffles)
-      int const csi = (int)(cq * ROW_WARPS) + __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0);
+      int const csi = (int)(cq * PER_CLAIM) + __shfl_sync(FULL_MASK, (int)(threadIdx.x >> 5), 0) * G + seg;
       active = csi < a.s.nseq;
       item = (unsigned long long)cpi * (unsigned)a.s.nseq + (active ? csi : 0);
       int const cp = a.s.class_profiles[cpi];

@@ -373,7 +373,7 @@ def test_bench_workload_sample_matches_compiled_reference(reference, node_pool):
         dev.close()
 
 
-@pytest.mark.parametrize("nseq", [4, 6, 9])
+@pytest.mark.parametrize("nseq", [4, 6, 9, 19, 40])
 def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, nseq):
     """score_grid runs the profile-stationary kernels (short-code rows and the null/background table
     staged in shared memory by TMA bulk copies, four reads of one profile per CTA) for one-warp
@@ -383,7 +383,9 @@ def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, nseq):
     consecutive claims of a CTA change profile.  Checked against the oracle on a sample."""
     from deciphon_b200.device import Device
     rng = np.random.default_rng(1000 + nseq)
-    sizes = [129, 150, 160, 161, 180, 192, 200, 230, 256, 257, 300, 400, 440, 520, 700, 760, 1000]  # every staged mode
+    # every staged mode and shape: whole profiles on 4 / 8 / 16 / 32 lanes, first / later segments, tails on 4..32 lanes
+    sizes = [129, 150, 160, 161, 180, 192, 200, 230, 256, 257, 300, 400, 440, 520, 700, 760, 1000,
+             5, 20, 24, 32, 33, 48, 64, 65, 90, 128, 260, 290, 330]
     reads = [synth.random_read(rng, int(rng.integers(200, 700))) for _ in range(nseq)]
     with Device(0) as dev:
         profs = [synth.synth_profile(rng, K, node_pool) for K in sizes]
