@@ -727,8 +727,9 @@ def run_b200(args, rank, local_rank, world):
                          "peak_measured_mix_source": "dcpgpu_alu_peak mode 6 on this GPU: FADD + three-input integer min 2:1 "
                                                      "(the row's own mix; a min3 counts as two of the 33 ops)",
                          "alu_probe": peaks,
-                         "kernel": "score pass of the first windows = score_row_kernel<Q,SEG,MODE> (row_kernel.cuh): whole "
-                                   "profiles of <= 256 nodes (SEG 32/16/8/4), 256-node segments + tail of larger ones "
+                         "kernel": "score pass of the first windows = score_row_kernel<Q,SEG,MODE,false,STAGE> (row_kernel.cuh, "
+                                   "profile-stationary CTAs, short-code rows + null/background table staged in shared memory by "
+                                   "TMA): whole profiles of <= 256 nodes (SEG 32/16/8/4), 256-node segments + tail of larger ones "
                                    "(speculative B, exact redo by score_reg_kernel<Q,W>), generic_kernel<false> for the rest; rank 0",
                          "ops_per_cell": OPS_PER_CELL, "kernel_gcups": kern["grid_cells"] / (kern["score_ms"] * 1e-3) / 1e9,
                          "kernel_ms_per_step": kern["score_ms"] / min(args.steps, 5),
