@@ -1105,11 +1105,17 @@ int dcpgpu_pool_add(dcpgpu_ctx *ctx, int nnodes, float const *emission, float co
     cudaFree(b.em);
     return fail_cuda(ctx, e, "cudaMalloc(pool trans)");
   }
+  e = counted_copy(ctx, b.em, emission, eb, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = counted_copy(ctx, b.trans, trans, tb, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess)
+  { // the block never becomes part of the pool
+    cudaFree(b.em);
+    cudaFree(b.trans);
+    return fail_cuda(ctx, e, "pool_add: upload");
+  }
   ctx->pool.push_back(b);
   ctx->pool_nodes += nnodes;
-  CU(counted_copy(ctx, b.em, emission, eb, cudaMemcpyHostToDevice, ctx->stream));
-  CU(counted_copy(ctx, b.trans, trans, tb, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
   if (first_node_id) *first_node_id = b.first;
   return 0;
 }
