@@ -538,7 +538,7 @@ int launch_class_t(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a)
 
 int launch_class(dcpgpu_ctx *ctx, int cls, ScoreArgs const &a) { return launch_class_t<false>(ctx, cls, a); }
 
-// ---- segmented profiles: level-by-level launches (strip_kernel.cuh, tail_kernel.cuh) ----------
+// ---- segmented profiles: level-by-level launches (row_kernel.cuh: FIRST / MID / LAST) ---------
 // kind of a segment launch: -2 = first full segment, -1 = later full segment, 0..15 = tail class
 // (0..3: full warp, Q = 5..8; 4..7: 16 lanes; 8..11: 8 lanes; 12..15: 4 lanes).
 int tail_class(ProfileDesc const &g)

@@ -32,7 +32,7 @@ struct ProfileDesc
   int W;    // warps per pair
   int Kpad; // VL * Q
   int VL;   // virtual lanes a row is striped over: 32 * W, or 16/8/4 for profiles of at most
-            // 128/64/32 nodes (two/four/eight pairs share a warp, sub_kernel.cuh)
+            // 128/64/32 nodes (two/four/eight pairs share a warp, row_kernel.cuh)
   int Kfull; // nodes of the whole profile when this describes one segment of it (strip_kernel.cuh), else K
 };
 
@@ -87,7 +87,7 @@ struct ReadsView
   int const *seq_len;        // [nseq]
   int nseq;
   int eight;                 // the value 8 as a run-time operand (row_kernel.cuh:mad_ptr)
-  long long nwords;          // words in the buffer (sub_kernel.cuh clamps its read-ahead to it)
+  long long nwords;          // words in the buffer (bounds of the packed stream)
 };
 
 } // namespace dcp

@@ -11,11 +11,12 @@
 // which is value-exact (bit-identical) with the reference because fp32 rounding is
 // monotone: min_i((s_i + tau_i) + e) == (min_i (s_i + tau_i)) + e.
 //
-// This file is the DP row and the exact kernel, W WARPS PER PAIR (W = 1 for K <= 256, 2/4/8 up
-// to K = 2048).  The score pass uses it as is for 128 < K <= 256; smaller profiles share a warp
-// (sub_kernel.cuh), larger ones are scored as speculative strips (strip_kernel.cuh,
-// tail_kernel.cuh) and come back here -- W = 2/4/8 -- only when the speculation fails, and for
-// the trace pass's value dump (DUMP).  The K nodes are
+// This file is the round-1 DP row and the exact kernel with W WARPS PER PAIR.  Since round 2 the
+// score pass runs the single-warp row of row_kernel.cuh for every profile of up to 256 nodes and
+// for the 256-node segments of larger ones (speculative B); profiles of 257..2048 nodes come
+// here -- W = 2/4/8 -- only when that speculation fails, and for the trace pass's value dump
+// (DUMP).  The shared types (Lane, Mail, ScoreArgs, DumpView, the TMA helpers) also live here.
+// The K nodes are
 // striped across the VL = 32*W "virtual lanes" like the reference stripes them across SIMD
 // lanes (viterbi.c:220-221): vl = k / Q, q = k % Q, Q <= 8.  Per lane everything lives in
 // registers:
