@@ -9,15 +9,16 @@ import sys
 def family(name):
     n = re.sub(r"^void ", "", name).replace("dcp::", "").replace("(anonymous namespace)::", "")
     n = n.replace("(int)", "").replace("(bool)", "")
-    m = re.match(r"score_row_kernel<(\d+), (\d+), (\d+), (\d)>", n)
+    m = re.match(r"score_row_kernel<(\d+), (\d+), (\d+), (\d)(?:, (\d))?>", n)
     if m:
-        q, seg, mode, dump = (int(x) for x in m.groups())
+        q, seg, mode, dump = (int(x) for x in m.groups()[:4])
+        stage = " staged" if m.group(5) == "1" else ""
         if dump:
             return "score_row_kernel<Q,SEG,WHOLE,DUMP> (trace: value dump)"
         if mode == 0:
-            return "score_row_kernel<Q,32,WHOLE> (128 < K <= 256)" if seg == 32 else "score_row_kernel<Q,16/8/4,WHOLE> (K <= 128)"
+            return ("score_row_kernel<Q,32,WHOLE> (128 < K <= 256)" if seg == 32 else "score_row_kernel<Q,16/8/4,WHOLE> (K <= 128)") + stage
         return {1: "score_row_kernel<8,32,FIRST> (first 256-node segment)", 2: "score_row_kernel<8,32,MID> (later full segments)",
-                3: "score_row_kernel<Q,SEG,LAST> (tail segments)"}[mode]
+                3: "score_row_kernel<Q,SEG,LAST> (tail segments)"}[mode] + stage
     m = re.match(r"score_reg_kernel<(\d+), (\d+), (\d)>", n)
     if m:
         return "score_reg_kernel<Q,W,DUMP> (trace: value dump, K > 256)" if m.group(3) == "1" else "score_reg_kernel<Q,W> (exact redo of failed speculation)"
