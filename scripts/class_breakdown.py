@@ -12,12 +12,13 @@ def shape(K):
     """(W, Q, G) as csrc/layout.cuh layout_shape assigns them."""
     if os.environ.get("DCPGPU_SUBWARP", "1") != "0" and K <= 128:
         vl = 4 if K <= 32 else 8 if K <= 64 else 16
-        return 1, max(5, -(-K // vl)), 32 // vl
+        q = max(5, -(-K // vl))
+        return 1, 8 if q == 7 else q, 32 // vl
     W = 1
     while 32 * W * 8 < K:
         W *= 2
     Q = -(-K // (32 * W))
-    return W, Q, 1
+    return W, 8 if (W == 1 and Q == 7) else Q, 1
 
 
 def main():
