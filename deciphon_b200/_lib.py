@@ -36,6 +36,7 @@ SYMBOLS = [
     ("dcpgpu_score_grid", C.c_int, [_vp, _i32, _i32, _i32, _i32, _u32]),
     ("dcpgpu_scores_fetch", C.c_int, [_vp, _i64, _vp, _vp]),
     ("dcpgpu_hits_fetch", C.c_int, [_vp, _i64, _vp, C.POINTER(_i64)]),
+    ("dcpgpu_scores_gather", C.c_int, [_vp, _i64, _vp, _vp, _vp]),
     ("dcpgpu_last_cells", C.c_double, [_vp]),
     ("dcpgpu_last_kernel_ms", _f32, [_vp]),
     ("dcpgpu_last_redo", _i64, [_vp]),

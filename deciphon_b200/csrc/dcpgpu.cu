@@ -353,6 +353,12 @@ __global__ void hits_fill_kernel(float2 const *out, long long n, unsigned long l
   }
 }
 
+__global__ void gather_scores_kernel(float2 const *out, long long const *idx, long long n, float2 *dst)
+{
+  long long const i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = out[idx[i]];
+}
+
 // The special transitions of one window (xtrans.c:21-68 with thread.c:112's max(L/3, 1)).
 // Same expressions as the reference: float operands, double log(), results stored to float.
 void host_xtrans(int window_len, bool multi_hits, bool hmmer3_compat, float *out)
@@ -1622,6 +1628,32 @@ int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t 
   std::sort(h.begin(), h.end());
   for (int64_t i = 0; i < std::min<int64_t>(cap, (int64_t)n); ++i)
     hit_index[i] = h[(size_t)i];
+  return 0;
+}
+
+int dcpgpu_scores_gather(dcpgpu_ctx *ctx, int64_t n, int64_t const *index, float *null_cost, float *alt_cost)
+{
+  if (!ctx || n < 0 || (n && !index)) return fail(ctx, DCPGPU_EINVAL, "scores_gather: bad argument");
+  if (n == 0) return 0;
+  for (int64_t i = 0; i < n; ++i)
+    if (index[i] < 0 || index[i] >= ctx->last_n) return fail(ctx, DCPGPU_EINVAL, "scores_gather: index out of range");
+  CU(cudaSetDevice(ctx->device));
+  int rc;
+  if ((rc = ensure(ctx, ctx->d_hit_idx, ctx->hit_idx_cap, (size_t)n))) return rc;
+  if ((rc = ensure(ctx, ctx->d_tout, ctx->tout_cap, (size_t)n))) return rc;
+  static_assert(sizeof(long long) == sizeof(int64_t), "index type");
+  CU(counted_copy(ctx, ctx->d_hit_idx, index, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  gather_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_hit_idx, (long long)n, ctx->d_tout);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  std::vector<float2> h((size_t)n);
+  CU(counted_copy(ctx, h.data(), ctx->d_tout, (size_t)n * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int64_t i = 0; i < n; ++i)
+  {
+    if (null_cost) null_cost[i] = h[(size_t)i].x;
+    if (alt_cost) alt_cost[i] = h[(size_t)i].y;
+  }
   return 0;
 }
 

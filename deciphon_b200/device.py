@@ -163,6 +163,14 @@ class Device:
             self._check(lib.dcpgpu_hits_fetch(self._h, n.value, _ptr(idx), C.byref(n)))
         return idx
 
+    def scores_gather(self, index: np.ndarray):
+        """(null_cost, alt_cost) of the given pairs of the last score pass (e.g. its hit list)."""
+        index = np.ascontiguousarray(index, dtype=np.int64)
+        nul = np.empty(len(index), dtype=np.float32)
+        alt = np.empty(len(index), dtype=np.float32)
+        self._check(lib.dcpgpu_scores_gather(self._h, len(index), _ptr(index), _ptr(nul), _ptr(alt)))
+        return nul, alt
+
     def last_cells(self) -> float:
         return float(lib.dcpgpu_last_cells(self._h))
 

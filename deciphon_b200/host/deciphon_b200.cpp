@@ -753,13 +753,8 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
     x->windows += (long)P * S;
     x->cells += (long long)cells; // first windows of the chunk (profile_cells above)
     x->lrt_windows += (long)nhits;
-    std::vector<float> nul0, alt0;
-    if (nhits)
-    {
-      nul0.resize((size_t)P * S);
-      alt0.resize((size_t)P * S);
-      if ((rc = dcpgpu_scores_fetch(gpu, (int64_t)P * S, nul0.data(), alt0.data()))) return map_gpu_error(rc);
-    }
+    std::vector<float> hn((size_t)nhits), ha((size_t)nhits); // costs of the hits only (not the whole P x S grid)
+    if (nhits && (rc = dcpgpu_scores_gather(gpu, nhits, hit.data(), hn.data(), ha.data()))) return map_gpu_error(rc);
 
     // pairs whose sequence is longer than the first window keep iterating (window.c:27-31)
     std::vector<Active> active;
@@ -777,15 +772,12 @@ int run_shard(dcp_scan *x, size_t shard_index, dcp_batch const *batch, std::vect
 
     std::vector<dcpgpu_pair> hp((size_t)nhits);
     std::vector<int> widx((size_t)nhits, 0);
-    std::vector<float> hn((size_t)nhits), ha((size_t)nhits);
     std::vector<Active *> owner((size_t)nhits, nullptr);
     for (int64_t i = 0; i < nhits; ++i)
     {
       int const p = l0 + (int)(hit[(size_t)i] / S), s = (int)(hit[(size_t)i] % S);
       int const len = (int)(offsets[(size_t)s + 1] - offsets[(size_t)s]);
       hp[(size_t)i] = dcpgpu_pair{p, s, 0, std::min(len, std::min(x->profiles[(size_t)(sh.p0 + p)].K * 50, 100000))};
-      hn[(size_t)i] = nul0[(size_t)hit[(size_t)i]];
-      ha[(size_t)i] = alt0[(size_t)hit[(size_t)i]];
       auto it = by_pair.find({p, s});
       if (it != by_pair.end()) owner[(size_t)i] = it->second;
     }

@@ -121,6 +121,9 @@ int dcpgpu_scores_fetch(dcpgpu_ctx *ctx, int64_t npairs, float *null_cost, float
 /* Indices (into the last score pass) of pairs with finite lrt >= 0 (thread.c:119-121),
  * ascending; returns their count through *nhits, writes at most cap of them. */
 int dcpgpu_hits_fetch(dcpgpu_ctx *ctx, int64_t cap, int64_t *hit_index, int64_t *nhits);
+/* The last score pass' results of the given pairs only (e.g. the hit_index list of
+ * dcpgpu_hits_fetch): null_cost[i], alt_cost[i] = costs of pair index[i]; synchronises. */
+int dcpgpu_scores_gather(dcpgpu_ctx *ctx, int64_t n, int64_t const *index, float *null_cost, float *alt_cost);
 /* DP cells (sum of len*K) of the last score pass, and device ms of its kernels. */
 double dcpgpu_last_cells(dcpgpu_ctx const *ctx);
 float dcpgpu_last_kernel_ms(dcpgpu_ctx *ctx);

@@ -405,3 +405,22 @@ def test_staged_grid_kernels_match_the_pair_kernels(oracle, node_pool, nseq):
             x = reads[s]
             xt = oracle.xtrans(len(x), True, False)
             assert _bits(ga[p * nseq + s:p * nseq + s + 1])[0] == _bits(oracle.alt(costs, xt, x).reshape(1))[0]
+
+
+def test_scores_gather_matches_the_full_fetch(device, golden_dev, ref_vectors):
+    """dcpgpu_scores_gather (what dcp_scan_run copies back: the hits' costs only) = the same entries of
+    dcpgpu_scores_fetch, bit for bit; out-of-range indices are refused."""
+    from deciphon_b200._lib import DcpGpuError
+    base, reads = golden_dev
+    device.set_reads(reads)
+    nprof, nseq = 3, len(reads)
+    device.score_grid(base, base + nprof, 0, nseq, True, False)
+    nul, alt = device.scores_fetch(nprof * nseq)
+    idx = np.asarray([0, nprof * nseq - 1, 5, 5, 2], dtype=np.int64)
+    gn, ga = device.scores_gather(idx)
+    assert np.array_equal(_bits(gn), _bits(nul[idx])) and np.array_equal(_bits(ga), _bits(alt[idx]))
+    hits = device.hits_fetch()
+    hn, ha = device.scores_gather(hits)
+    assert np.array_equal(_bits(hn), _bits(nul[hits])) and np.array_equal(_bits(ha), _bits(alt[hits]))
+    with pytest.raises(DcpGpuError):
+        device.scores_gather(np.asarray([nprof * nseq], dtype=np.int64))
