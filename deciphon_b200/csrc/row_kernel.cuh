@@ -247,7 +247,7 @@ template <int Q, int SEG, int MODE, bool DUMP, int J, class EM>
 __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EM const &em, float2 const *nulbg,
                                        uint32_t eight, uint32_t h, uint32_t hn, int sl, float NB, float EB, float JB, float4 &bnext,
                                        float4 &bnext2, Mail *slot, float &E, float &x, bool &ok, DumpRef<DUMP> const &dv, int l,
-                                       bool in_window)
+                                       bool in_window, bool own)
 {
   constexpr int s1 = (J + 4) % 5, s2 = (J + 3) % 5, s3 = (J + 2) % 5, s4 = (J + 1) % 5;
   constexpr bool HEAD_IN = MODE == ROW_MID || MODE == ROW_LAST;  // lane 0's predecessor is the previous segment
@@ -376,8 +376,9 @@ __device__ __forceinline__ void row_v2(Lane<Q> &s, Partial<Q> &pt, EM const &em,
   }
 
   if constexpr (COL_OUT)
-  {
-    if (sl == SEG - 1) __stcg(reinterpret_cast<float4 *>(slot), make_float4(M[Q - 1], I[Q - 1], D[Q - 1], e));
+  { // (a lane group that only shadows another pair must not touch that pair's column: a later full
+    // segment rewrites it in place while its owner is still reading ahead)
+    if (own && sl == SEG - 1) __stcg(reinterpret_cast<float4 *>(slot), make_float4(M[Q - 1], I[Q - 1], D[Q - 1], e));
   }
 
   if constexpr (DUMP)
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(32 * ROW_WARPS, row_min_blocks<Q, SEG, MODE, D
     if (l > Lmax) break;                                                                         \
     uint32_t const hn = __ldg(hp + (I_) + 1);                                                    \
     row_v2<Q, SEG, MODE, DUMP, JJ_>(s, pt, em, pd.nulbg, eight, h, hn, sl, NB, EB, JB, bnext, bnext2, col + l, E, x, ok, dv, l,  \
-                                    l <= L);                                                     \
+                                    l <= L, active);                                             \
     if (SEG != 32 && l == L)                                                                     \
     {                                                                                            \
       Eres = E;                                                                                  \
